@@ -1,0 +1,579 @@
+// C-ABI of the engine (declarations and reference citations: include/cosyb200.h).
+#include <cstdarg>
+#include <cstring>
+#include <map>
+#include <string>
+
+#include "common.h"
+#include "effnet_table.h"
+#include "kernels_backbone.cuh"
+#include "kernels_crop.cuh"
+#include "kernels_geometry.cuh"
+#include "kernels_ransac.cuh"
+
+namespace cosyb {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+  }
+  ~DeviceGuard() {
+    int cur = -1;
+    cudaGetDevice(&cur);
+    if (prev >= 0 && cur != prev) cudaSetDevice(prev);
+  }
+};
+
+static int dev_alloc(void** p, size_t bytes) {
+  CB_CUDA(cudaMalloc(p, bytes ? bytes : 16));
+  return 0;
+}
+
+static int upload(PoseModel& m, float** dst, const std::vector<float>& v) {
+  void* p = nullptr;
+  int rc = dev_alloc(&p, v.size() * sizeof(float));
+  if (rc) return rc;
+  m.allocs.push_back(p);
+  CB_CUDA(cudaMemcpy(p, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice));
+  *dst = (float*)p;
+  return 0;
+}
+
+static void free_model(PoseModel& m) {
+  for (void* p : m.allocs) cudaFree(p);
+  m = PoseModel();
+}
+
+// ---- GEMM dispatch --------------------------------------------------------------------------
+template <int BM, int BN, int TM, int TN>
+static void launch_gemm_tile(bool gate, bool swish, bool resid, const float* A, const float* Wkn,
+                             const float* bias, const float* g, const float* r, float* C, int M,
+                             int N, int K, int rows_per_img, cudaStream_t st) {
+  dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
+  if (!gate && swish && !resid)
+    k_pw_gemm<BM, BN, TM, TN, false, true, false><<<grid, GEMM_THREADS, 0, st>>>(A, Wkn, bias, g, r, C, M, N, K, rows_per_img);
+  else if (gate && !swish && !resid)
+    k_pw_gemm<BM, BN, TM, TN, true, false, false><<<grid, GEMM_THREADS, 0, st>>>(A, Wkn, bias, g, r, C, M, N, K, rows_per_img);
+  else if (gate && !swish && resid)
+    k_pw_gemm<BM, BN, TM, TN, true, false, true><<<grid, GEMM_THREADS, 0, st>>>(A, Wkn, bias, g, r, C, M, N, K, rows_per_img);
+}
+
+static void launch_gemm(bool gate, bool swish, bool resid, const float* A, const float* Wkn,
+                        const float* bias, const float* g, const float* r, float* C, int M, int N,
+                        int K, int rows_per_img, cudaStream_t st) {
+  // pick the N tile with the least padded work per unit of kernel efficiency
+  const int bns[3] = {32, 64, 128};
+  const float eff[3] = {0.6f, 0.8f, 1.0f};
+  int best = 0;
+  float best_cost = 1e30f;
+  for (int i = 0; i < 3; ++i) {
+    float cost = float((N + bns[i] - 1) / bns[i] * bns[i]) / eff[i];
+    if (cost < best_cost - 1e-6f) { best_cost = cost; best = i; }
+  }
+  if (best == 0) launch_gemm_tile<128, 32, 4, 4>(gate, swish, resid, A, Wkn, bias, g, r, C, M, N, K, rows_per_img, st);
+  else if (best == 1) launch_gemm_tile<128, 64, 8, 4>(gate, swish, resid, A, Wkn, bias, g, r, C, M, N, K, rows_per_img, st);
+  else launch_gemm_tile<128, 128, 8, 8>(gate, swish, resid, A, Wkn, bias, g, r, C, M, N, K, rows_per_img, st);
+}
+
+// ---- depthwise dispatch ---------------------------------------------------------------------
+struct DwPlan { int n_chunks, Gc, P, pix_per_tile, tiles; };
+static DwPlan dw_plan(const BlockSpec& b) {
+  DwPlan p;
+  int G = b.cexp / 4;
+  p.n_chunks = (G + DW_MAX_THREADS - 1) / DW_MAX_THREADS;
+  while (G % p.n_chunks) ++p.n_chunks;
+  p.Gc = G / p.n_chunks;
+  p.P = DW_MAX_THREADS / p.Gc;
+  p.pix_per_tile = 128;
+  p.tiles = (b.hout * b.wout + p.pix_per_tile - 1) / p.pix_per_tile;
+  return p;
+}
+
+static int launch_dw(const BlockSpec& b, const BlockWeights& w, const float* in, float* out,
+                     float* partial, int B, cudaStream_t st) {
+  DwPlan p = dw_plan(b);
+  dim3 grid(p.tiles, p.n_chunks, B);
+  int threads = p.Gc * p.P;
+#define DW_ARGS in, w.dw_w, w.dw_bias, out, partial, b.hin, b.win, b.cexp, b.hout, b.wout, b.pad_lo, p.Gc, p.P, p.pix_per_tile, p.tiles
+  if (b.k == 3 && b.s == 1) k_dwconv<3, 1><<<grid, threads, 0, st>>>(DW_ARGS);
+  else if (b.k == 3 && b.s == 2) k_dwconv<3, 2><<<grid, threads, 0, st>>>(DW_ARGS);
+  else if (b.k == 5 && b.s == 1) k_dwconv<5, 1><<<grid, threads, 0, st>>>(DW_ARGS);
+  else if (b.k == 5 && b.s == 2) k_dwconv<5, 2><<<grid, threads, 0, st>>>(DW_ARGS);
+  else { set_error("unsupported depthwise k=%d s=%d", b.k, b.s); return COSYB200_EINVAL; }
+#undef DW_ARGS
+  CB_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---- trunk forward --------------------------------------------------------------------------
+static int net_forward(cosyb200_handle* h, int slot, int B, const float* crops, const float* renders,
+                       float* pose9, float* const* taps, const float* TCO_in, const float* K_crop,
+                       float* TCO_out, cudaStream_t st) {
+  const PoseModel& m = h->models[slot];
+  {
+    dim3 grid(RENDER_W / 2 / STEM_TX, RENDER_H / 2 / STEM_TY, B), block(STEM_TX, STEM_TY);
+    k_stem<<<grid, block, 0, st>>>(crops, renders, m.stem_w, m.stem_bias, h->act[0]);
+    CB_LAUNCH_CHECK();
+  }
+  int cur = 0;
+  auto tap = [&](int i, const float* src, size_t n) -> int {
+    if (taps && taps[i]) CB_CUDA(cudaMemcpyAsync(taps[i], src, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return 0;
+  };
+  int rc = tap(0, h->act[0], (size_t)B * (RENDER_H / 2) * (RENDER_W / 2) * STEM_OUT);
+  if (rc) return rc;
+  for (size_t i = 0; i < h->blocks.size(); ++i) {
+    const BlockSpec& b = h->blocks[i];
+    const BlockWeights& w = m.blocks[i];
+    const float* x = h->act[cur];
+    float* y = h->act[cur ^ 1];
+    const int Min = B * b.hin * b.win, Mout = B * b.hout * b.wout;
+    const float* dw_in = x;
+    if (b.e != 1) {
+      launch_gemm(false, true, false, x, w.expand_kn, w.expand_bias, nullptr, nullptr, h->buf_e, Min,
+                  b.cexp, b.cin, 1, st);
+      CB_LAUNCH_CHECK();
+      dw_in = h->buf_e;
+    }
+    rc = launch_dw(b, w, dw_in, h->buf_d, h->pool_partial, B, st);
+    if (rc) return rc;
+    DwPlan p = dw_plan(b);
+    k_se_gate<<<B, SE_THREADS, 0, st>>>(h->pool_partial, p.tiles, b.cexp, b.cse,
+                                        1.0f / float(b.hout * b.wout), w.se_r_w, w.se_r_b, w.se_e_w,
+                                        w.se_e_b, h->gate);
+    CB_LAUNCH_CHECK();
+    launch_gemm(true, false, b.skip != 0, h->buf_d, w.proj_kn, w.proj_bias, h->gate, x, y, Mout, b.cout,
+                b.cexp, b.hout * b.wout, st);
+    CB_LAUNCH_CHECK();
+    cur ^= 1;
+    rc = tap(1 + (int)i, y, (size_t)Mout * b.cout);
+    if (rc) return rc;
+  }
+  const BlockSpec& last = h->blocks.back();
+  const int n_pos = last.hout * last.wout;
+  launch_gemm(false, true, false, h->act[cur], m.head_kn, m.head_bias, nullptr, nullptr, h->buf_e,
+              B * n_pos, N_FEATURES, last.cout, 1, st);
+  CB_LAUNCH_CHECK();
+  rc = tap(1 + (int)h->blocks.size(), h->buf_e, (size_t)B * n_pos * N_FEATURES);
+  if (rc) return rc;
+  k_pool_fc_update<<<B, HEAD_THREADS, 0, st>>>(h->buf_e, n_pos, m.fc_w, m.fc_b, pose9, TCO_in, K_crop, TCO_out);
+  CB_LAUNCH_CHECK();
+  return 0;
+}
+
+static int check_batch(cosyb200_handle* h, int B, const char* fn) {
+  CB_CHECK_ARG(h != nullptr, "%s: null handle", fn);
+  CB_CHECK_ARG(B >= 1 && B <= h->max_batch, "%s: batch %d outside [1, %d]", fn, B, h->max_batch);
+  return 0;
+}
+
+}  // namespace cosyb
+
+using namespace cosyb;
+
+extern "C" {
+
+const char* cosyb200_last_error(void) { return g_err; }
+int cosyb200_version(void) { return 100; }
+
+int cosyb200_effnet_block(int idx, int32_t* out) {
+  static const std::vector<BlockSpec> blocks = make_effnet_b3();
+  CB_CHECK_ARG(out != nullptr && idx >= 0 && idx < (int)blocks.size(), "effnet_block: bad index %d", idx);
+  const BlockSpec& b = blocks[idx];
+  int32_t v[11] = {b.k, b.s, b.e, b.cin, b.cexp, b.cse, b.cout, b.pad_lo, b.pad_hi, b.skip, (int32_t)blocks.size()};
+  memcpy(out, v, sizeof(v));
+  return COSYB200_OK;
+}
+
+int cosyb200_create(cosyb200_handle** out, int device, int max_batch) {
+  CB_CHECK_ARG(out != nullptr, "create: null out");
+  CB_CHECK_ARG(max_batch >= 1 && max_batch <= 4096, "create: max_batch %d outside [1, 4096]", max_batch);
+  int n_dev = 0;
+  CB_CUDA(cudaGetDeviceCount(&n_dev));
+  CB_CHECK_ARG(device >= 0 && device < n_dev, "create: device %d not present (%d devices)", device, n_dev);
+  DeviceGuard guard(device);
+  cudaDeviceProp prop;
+  CB_CUDA(cudaGetDeviceProperties(&prop, device));
+  CB_CHECK_ARG(prop.major == 10, "create: device %d is sm_%d%d; this engine is built for sm_100a only",
+               device, prop.major, prop.minor);
+  cosyb200_handle* h = new cosyb200_handle();
+  h->device = device;
+  h->max_batch = max_batch;
+  h->n_sms = prop.multiProcessorCount;
+  h->blocks = make_effnet_b3();
+  size_t act = (size_t)(RENDER_H / 2) * (RENDER_W / 2) * STEM_OUT, e = 0, d = 0, part = 0, cmax = 0;
+  for (const BlockSpec& b : h->blocks) {
+    act = std::max(act, (size_t)b.hout * b.wout * b.cout);
+    if (b.e != 1) e = std::max(e, (size_t)b.hin * b.win * b.cexp);
+    d = std::max(d, (size_t)b.hout * b.wout * b.cexp);
+    part = std::max(part, (size_t)dw_plan(b).tiles * b.cexp);
+    cmax = std::max(cmax, (size_t)b.cexp);
+  }
+  e = std::max(e, (size_t)h->blocks.back().hout * h->blocks.back().wout * N_FEATURES);
+  h->act_elems = act; h->e_elems = e; h->d_elems = d; h->partial_elems = part;
+  const size_t B = (size_t)max_batch;
+  int rc = 0;
+  rc |= dev_alloc((void**)&h->act[0], B * act * 4);
+  rc |= dev_alloc((void**)&h->act[1], B * act * 4);
+  rc |= dev_alloc((void**)&h->buf_e, B * e * 4);
+  rc |= dev_alloc((void**)&h->buf_d, B * d * 4);
+  rc |= dev_alloc((void**)&h->pool_partial, B * part * 4);
+  rc |= dev_alloc((void**)&h->gate, B * cmax * 4);
+  rc |= dev_alloc((void**)&h->crops, B * 3 * RENDER_H * RENDER_W * 4);
+  rc |= dev_alloc((void**)&h->pose9, B * POSE_DIM * 4);
+  if (rc) { cosyb200_destroy(h); return COSYB200_ENOMEM; }
+  *out = h;
+  return COSYB200_OK;
+}
+
+int cosyb200_destroy(cosyb200_handle* h) {
+  if (!h) return COSYB200_OK;
+  DeviceGuard guard(h->device);
+  free_model(h->models[0]);
+  free_model(h->models[1]);
+  void* ptrs[] = {h->act[0], h->act[1], h->buf_e, h->buf_d, h->pool_partial, h->gate, h->crops, h->pose9,
+                  h->pts_sampled, h->sym, h->n_sym, h->aabb};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  delete h;
+  return COSYB200_OK;
+}
+
+int cosyb200_load_pose_model(cosyb200_handle* h, int slot, int n, const char* const* names,
+                             const float* const* ptrs, const int64_t* numels) {
+  CB_CHECK_ARG(h != nullptr, "load_pose_model: null handle");
+  CB_CHECK_ARG(slot == 0 || slot == 1, "load_pose_model: slot %d", slot);
+  CB_CHECK_ARG(n > 0 && names && ptrs && numels, "load_pose_model: empty state dict");
+  DeviceGuard guard(h->device);
+  std::map<std::string, std::pair<const float*, int64_t>> sd;
+  for (int i = 0; i < n; ++i) sd[names[i]] = {ptrs[i], numels[i]};
+  bool ok = true;
+  std::string missing;
+  auto get = [&](const std::string& key, int64_t numel) -> const float* {
+    auto it = sd.find(key);
+    if (it == sd.end() || it->second.second != numel || it->second.first == nullptr) {
+      if (ok) missing = key + (it == sd.end() ? " (missing)" : " (wrong size)");
+      ok = false;
+      return nullptr;
+    }
+    return it->second.first;
+  };
+  // BN eval: y = x * g/sqrt(var+eps) + (b - mean * g/sqrt(var+eps))
+  auto bn_fold = [&](const std::string& prefix, int c, std::vector<float>& scale, std::vector<float>& shift) {
+    const float* g = get(prefix + ".weight", c);
+    const float* b = get(prefix + ".bias", c);
+    const float* mu = get(prefix + ".running_mean", c);
+    const float* var = get(prefix + ".running_var", c);
+    scale.assign(c, 1.f);
+    shift.assign(c, 0.f);
+    if (!g || !b || !mu || !var) return;
+    for (int i = 0; i < c; ++i) {
+      float inv = 1.0f / sqrtf(var[i] + BN_EPS);
+      float a = g[i] * inv;
+      scale[i] = a;
+      shift[i] = b[i] - mu[i] * a;
+    }
+  };
+  // [N][K] row-scaled + its transpose
+  auto pack_pw = [&](const float* W, int N, int K, const std::vector<float>& scale, std::vector<float>& nk,
+                     std::vector<float>& kn) {
+    nk.assign((size_t)N * K, 0.f);
+    kn.assign((size_t)N * K, 0.f);
+    if (!W) return;
+    for (int o = 0; o < N; ++o)
+      for (int k = 0; k < K; ++k) {
+        float v = W[(size_t)o * K + k] * scale[o];
+        nk[(size_t)o * K + k] = v;
+        kn[(size_t)k * N + o] = v;
+      }
+  };
+
+  PoseModel m;
+  m.blocks.resize(h->blocks.size());
+  std::vector<float> scale, shift, nk, kn, tmp;
+  int rc = 0;
+  {
+    const float* W = get("backbone._conv_stem.weight", (int64_t)STEM_OUT * IN_CH * 9);
+    bn_fold("backbone._bn0", STEM_OUT, scale, shift);
+    tmp.assign(54 * STEM_OUT, 0.f);
+    if (W)
+      for (int co = 0; co < STEM_OUT; ++co)
+        for (int ci = 0; ci < IN_CH; ++ci)
+          for (int t = 0; t < 9; ++t)
+            tmp[(t * IN_CH + ci) * STEM_OUT + co] = W[((size_t)co * IN_CH + ci) * 9 + t] * scale[co];
+    rc |= upload(m, &m.stem_w, tmp);
+    rc |= upload(m, &m.stem_bias, shift);
+  }
+  for (size_t i = 0; i < h->blocks.size() && !rc; ++i) {
+    const BlockSpec& b = h->blocks[i];
+    BlockWeights& w = m.blocks[i];
+    const std::string p = "backbone._blocks." + std::to_string(i);
+    if (b.e != 1) {
+      const float* W = get(p + "._expand_conv.weight", (int64_t)b.cexp * b.cin);
+      bn_fold(p + "._bn0", b.cexp, scale, shift);
+      pack_pw(W, b.cexp, b.cin, scale, nk, kn);
+      rc |= upload(m, &w.expand_nk, nk);
+      rc |= upload(m, &w.expand_kn, kn);
+      rc |= upload(m, &w.expand_bias, shift);
+    }
+    {
+      const int kk = b.k * b.k;
+      const float* W = get(p + "._depthwise_conv.weight", (int64_t)b.cexp * kk);
+      bn_fold(p + "._bn1", b.cexp, scale, shift);
+      tmp.assign((size_t)kk * b.cexp, 0.f);
+      if (W)
+        for (int c = 0; c < b.cexp; ++c)
+          for (int t = 0; t < kk; ++t) tmp[(size_t)t * b.cexp + c] = W[(size_t)c * kk + t] * scale[c];
+      rc |= upload(m, &w.dw_w, tmp);
+      rc |= upload(m, &w.dw_bias, shift);
+    }
+    {
+      auto copy_up = [&](const std::string& key, int64_t numel, float** dst) {
+        const float* src = get(key, numel);
+        tmp.assign((size_t)numel, 0.f);
+        if (src) memcpy(tmp.data(), src, (size_t)numel * 4);
+        rc |= upload(m, dst, tmp);
+      };
+      copy_up(p + "._se_reduce.weight", (int64_t)b.cse * b.cexp, &w.se_r_w);
+      copy_up(p + "._se_reduce.bias", b.cse, &w.se_r_b);
+      copy_up(p + "._se_expand.weight", (int64_t)b.cexp * b.cse, &w.se_e_w);
+      copy_up(p + "._se_expand.bias", b.cexp, &w.se_e_b);
+    }
+    {
+      const float* W = get(p + "._project_conv.weight", (int64_t)b.cout * b.cexp);
+      bn_fold(p + "._bn2", b.cout, scale, shift);
+      pack_pw(W, b.cout, b.cexp, scale, nk, kn);
+      rc |= upload(m, &w.proj_nk, nk);
+      rc |= upload(m, &w.proj_kn, kn);
+      rc |= upload(m, &w.proj_bias, shift);
+    }
+  }
+  if (!rc) {
+    const int cin = h->blocks.back().cout;
+    const float* W = get("backbone._conv_head.weight", (int64_t)N_FEATURES * cin);
+    bn_fold("backbone._bn1", N_FEATURES, scale, shift);
+    pack_pw(W, N_FEATURES, cin, scale, nk, kn);
+    rc |= upload(m, &m.head_nk, nk);
+    rc |= upload(m, &m.head_kn, kn);
+    rc |= upload(m, &m.head_bias, shift);
+    const float* fw = get("pose_fc.weight", (int64_t)POSE_DIM * N_FEATURES);
+    const float* fb = get("pose_fc.bias", POSE_DIM);
+    tmp.assign((size_t)POSE_DIM * N_FEATURES, 0.f);
+    if (fw) memcpy(tmp.data(), fw, tmp.size() * 4);
+    rc |= upload(m, &m.fc_w, tmp);
+    tmp.assign(POSE_DIM, 0.f);
+    if (fb) memcpy(tmp.data(), fb, POSE_DIM * 4);
+    rc |= upload(m, &m.fc_b, tmp);
+  }
+  if (rc) { free_model(m); return rc; }
+  if (!ok) {
+    free_model(m);
+    set_error("load_pose_model: state_dict entry %s", missing.c_str());
+    return COSYB200_EINVAL;
+  }
+  free_model(h->models[slot]);
+  m.loaded = true;
+  h->models[slot] = m;
+  return COSYB200_OK;
+}
+
+int cosyb200_set_meshes(cosyb200_handle* h, int n_labels, int n_points, const float* points,
+                        int n_sample, const int64_t* point_ids, int s_max, const float* sym,
+                        const int32_t* n_sym, const float* aabb) {
+  CB_CHECK_ARG(h != nullptr, "set_meshes: null handle");
+  CB_CHECK_ARG(n_labels >= 1 && s_max >= 1 && sym && n_sym && aabb, "set_meshes: bad tables");
+  CB_CHECK_ARG((points == nullptr) || (n_sample == N_SAMPLE && point_ids && n_points >= n_sample),
+               "set_meshes: need %d sampled point ids out of >= %d points", N_SAMPLE, N_SAMPLE);
+  DeviceGuard guard(h->device);
+  for (void* p : {(void*)h->pts_sampled, (void*)h->sym, (void*)h->n_sym, (void*)h->aabb}) if (p) cudaFree(p);
+  h->pts_sampled = nullptr; h->sym = nullptr; h->n_sym = nullptr; h->aabb = nullptr;
+  h->n_labels = n_labels;
+  h->s_max = s_max;
+  for (int l = 0; l < n_labels; ++l)
+    CB_CHECK_ARG(n_sym[l] >= 1 && n_sym[l] <= s_max, "set_meshes: n_sym[%d]=%d outside [1,%d]", l, n_sym[l], s_max);
+  if (points) {
+    std::vector<float> ps((size_t)n_labels * N_SAMPLE * 3);
+    for (int l = 0; l < n_labels; ++l)
+      for (int i = 0; i < N_SAMPLE; ++i) {
+        int64_t id = point_ids[i];
+        CB_CHECK_ARG(id >= 0 && id < n_points, "set_meshes: point id %lld out of range", (long long)id);
+        memcpy(&ps[((size_t)l * N_SAMPLE + i) * 3], &points[((size_t)l * n_points + id) * 3], 12);
+      }
+    CB_CUDA(cudaMalloc((void**)&h->pts_sampled, ps.size() * 4));
+    CB_CUDA(cudaMemcpy(h->pts_sampled, ps.data(), ps.size() * 4, cudaMemcpyHostToDevice));
+  }
+  CB_CUDA(cudaMalloc((void**)&h->sym, (size_t)n_labels * s_max * 64));
+  CB_CUDA(cudaMemcpy(h->sym, sym, (size_t)n_labels * s_max * 64, cudaMemcpyHostToDevice));
+  CB_CUDA(cudaMalloc((void**)&h->n_sym, (size_t)n_labels * 4));
+  CB_CUDA(cudaMemcpy(h->n_sym, n_sym, (size_t)n_labels * 4, cudaMemcpyHostToDevice));
+  CB_CUDA(cudaMalloc((void**)&h->aabb, (size_t)n_labels * 96));
+  CB_CUDA(cudaMemcpy(h->aabb, aabb, (size_t)n_labels * 96, cudaMemcpyHostToDevice));
+  return COSYB200_OK;
+}
+
+#define NEED_MESH_PTS(fn) CB_CHECK_ARG(h->pts_sampled != nullptr, fn ": meshes not set");
+
+int cosyb200_tco_init(cosyb200_handle* h, int B, int zup, const float* boxes, const float* K,
+                      const int32_t* label_ids, float* TCO, void* stream) {
+  if (int rc = check_batch(h, B, "tco_init")) return rc;
+  if (zup) { if (!h->pts_sampled) { set_error("tco_init: meshes not set"); return COSYB200_ESTATE; } }
+  DeviceGuard guard(h->device);
+  k_tco_init<<<B, GEO_THREADS, 0, (cudaStream_t)stream>>>(B, zup, boxes, K, label_ids, h->pts_sampled, N_SAMPLE, TCO);
+  CB_LAUNCH_CHECK();
+  return COSYB200_OK;
+}
+
+int cosyb200_prepare_iter(cosyb200_handle* h, int B, int img_h, int img_w, const float* K,
+                          const float* TCO, const int32_t* label_ids, float* boxes_rend,
+                          float* boxes_crop, float* K_crop, void* stream) {
+  if (int rc = check_batch(h, B, "prepare_iter")) return rc;
+  if (!h->pts_sampled) { set_error("prepare_iter: meshes not set"); return COSYB200_ESTATE; }
+  CB_CHECK_ARG(img_h > 0 && img_w > 0, "prepare_iter: image size");
+  DeviceGuard guard(h->device);
+  float aspect = (float)((double)std::max(img_h, img_w) / (double)std::min(img_h, img_w));
+  k_project_boxes<<<B, GEO_THREADS, 0, (cudaStream_t)stream>>>(B, K, TCO, label_ids, h->pts_sampled, N_SAMPLE,
+                                                              aspect, boxes_rend, boxes_crop, K_crop);
+  CB_LAUNCH_CHECK();
+  return COSYB200_OK;
+}
+
+static int launch_crop(int B, const float* images, int n_images, int img_h, int img_w,
+                       const int32_t* im_ids, const float* boxes_crop, float* crops, cudaStream_t st) {
+  dim3 grid((RENDER_W + CROP_TX - 1) / CROP_TX, (RENDER_H + CROP_TY - 1) / CROP_TY, B), block(CROP_TX, CROP_TY);
+  k_roi_crop<<<grid, block, 0, st>>>(B, images, n_images, img_h, img_w, im_ids, boxes_crop, crops);
+  CB_LAUNCH_CHECK();
+  return 0;
+}
+
+int cosyb200_roi_crop(cosyb200_handle* h, int B, const float* images, int n_images, int img_h,
+                      int img_w, const int32_t* im_ids, const float* boxes_crop, float* crops,
+                      void* stream) {
+  CB_CHECK_ARG(h != nullptr && B >= 1, "roi_crop: bad arguments");
+  CB_CHECK_ARG(n_images >= 1 && img_h >= 2 && img_w >= 2, "roi_crop: image size");
+  DeviceGuard guard(h->device);
+  return launch_crop(B, images, n_images, img_h, img_w, im_ids, boxes_crop, crops, (cudaStream_t)stream);
+}
+
+int cosyb200_net_forward(cosyb200_handle* h, int slot, int B, const float* crops, const float* renders,
+                         float* pose9, float* const* taps, void* stream) {
+  if (int rc = check_batch(h, B, "net_forward")) return rc;
+  CB_CHECK_ARG(slot == 0 || slot == 1, "net_forward: slot %d", slot);
+  if (!h->models[slot].loaded) { set_error("net_forward: model slot %d not loaded", slot); return COSYB200_ESTATE; }
+  DeviceGuard guard(h->device);
+  return net_forward(h, slot, B, crops, renders, pose9, taps, nullptr, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+int cosyb200_update_pose(cosyb200_handle* h, int B, const float* TCO_in, const float* K_crop,
+                         const float* pose9, float* TCO_out, void* stream) {
+  CB_CHECK_ARG(h != nullptr && B >= 1, "update_pose: bad arguments");
+  DeviceGuard guard(h->device);
+  k_update_pose<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(B, TCO_in, K_crop, pose9, TCO_out);
+  CB_LAUNCH_CHECK();
+  return COSYB200_OK;
+}
+
+int cosyb200_refine_iter(cosyb200_handle* h, int slot, int B, const float* images, int n_images,
+                         int img_h, int img_w, const int32_t* im_ids, const float* boxes_crop,
+                         const float* renders, const float* K_crop, const float* TCO_in, float* pose9,
+                         float* TCO_out, void* stream) {
+  if (int rc = check_batch(h, B, "refine_iter")) return rc;
+  CB_CHECK_ARG(slot == 0 || slot == 1, "refine_iter: slot %d", slot);
+  if (!h->models[slot].loaded) { set_error("refine_iter: model slot %d not loaded", slot); return COSYB200_ESTATE; }
+  DeviceGuard guard(h->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int rc = launch_crop(B, images, n_images, img_h, img_w, im_ids, boxes_crop, h->crops, st)) return rc;
+  return net_forward(h, slot, B, h->crops, renders, pose9 ? pose9 : h->pose9, nullptr, TCO_in, K_crop, TCO_out, st);
+}
+
+int cosyb200_refine_n(cosyb200_handle* h, int slot, int B, int n_iter, const float* images,
+                      int n_images, int img_h, int img_w, const int32_t* im_ids, const float* K,
+                      const int32_t* label_ids, const float* renders, const float* TCO_in,
+                      float* TCO_out, float* K_crop, float* boxes_rend, float* boxes_crop,
+                      float* pose9, void* stream) {
+  if (int rc = check_batch(h, B, "refine_n")) return rc;
+  CB_CHECK_ARG(n_iter >= 1, "refine_n: n_iter %d", n_iter);
+  for (int n = 0; n < n_iter; ++n) {
+    const float* tin = n == 0 ? TCO_in : TCO_out + (size_t)(n - 1) * B * 16;
+    int rc = cosyb200_prepare_iter(h, B, img_h, img_w, K, tin, label_ids, boxes_rend + (size_t)n * B * 4,
+                                   boxes_crop + (size_t)n * B * 4, K_crop + (size_t)n * B * 9, stream);
+    if (rc) return rc;
+    rc = cosyb200_refine_iter(h, slot, B, images, n_images, img_h, img_w, im_ids,
+                              boxes_crop + (size_t)n * B * 4, renders + (size_t)n * B * 3 * RENDER_H * RENDER_W,
+                              K_crop + (size_t)n * B * 9, tin, pose9 + (size_t)n * B * POSE_DIM,
+                              TCO_out + (size_t)n * B * 16, stream);
+    if (rc) return rc;
+  }
+  return COSYB200_OK;
+}
+
+// ---- multiview ------------------------------------------------------------------------------
+static int pick_gs(int s_max) {
+  int gs = 1;
+  while (gs < s_max && gs < 32) gs <<= 1;
+  return gs;
+}
+
+#define DISPATCH_GS(gs, KERNEL, n_rows, ...)                                              \
+  do {                                                                                    \
+    int64_t threads_ = (int64_t)(n_rows) * (gs);                                          \
+    unsigned blocks_ = (unsigned)((threads_ + RANSAC_THREADS - 1) / RANSAC_THREADS);      \
+    switch (gs) {                                                                         \
+      case 1: KERNEL<1><<<blocks_, RANSAC_THREADS, 0, st>>>(__VA_ARGS__); break;          \
+      case 2: KERNEL<2><<<blocks_, RANSAC_THREADS, 0, st>>>(__VA_ARGS__); break;          \
+      case 4: KERNEL<4><<<blocks_, RANSAC_THREADS, 0, st>>>(__VA_ARGS__); break;          \
+      case 8: KERNEL<8><<<blocks_, RANSAC_THREADS, 0, st>>>(__VA_ARGS__); break;          \
+      case 16: KERNEL<16><<<blocks_, RANSAC_THREADS, 0, st>>>(__VA_ARGS__); break;        \
+      default: KERNEL<32><<<blocks_, RANSAC_THREADS, 0, st>>>(__VA_ARGS__); break;        \
+    }                                                                                     \
+  } while (0)
+
+int cosyb200_ransac_models(cosyb200_handle* h, int64_t n_seeds, const float* poses,
+                           const int32_t* cand_labels, const int32_t* seeds, float* TC1C2, void* stream) {
+  CB_CHECK_ARG(h != nullptr && n_seeds >= 0, "ransac_models: bad arguments");
+  if (!h->sym) { set_error("ransac_models: meshes not set"); return COSYB200_ESTATE; }
+  if (n_seeds == 0) return COSYB200_OK;
+  DeviceGuard guard(h->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  int gs = pick_gs(h->s_max);
+  DISPATCH_GS(gs, k_ransac_models, n_seeds, n_seeds, poses, cand_labels, seeds, h->aabb, h->sym, h->n_sym, h->s_max, TC1C2);
+  CB_LAUNCH_CHECK();
+  return COSYB200_OK;
+}
+
+int cosyb200_ransac_score(cosyb200_handle* h, int64_t n, const float* poses, const int32_t* cand_labels,
+                          const int32_t* tmatches, const float* TC1C2, float* dists, void* stream) {
+  CB_CHECK_ARG(h != nullptr && n >= 0, "ransac_score: bad arguments");
+  if (!h->sym) { set_error("ransac_score: meshes not set"); return COSYB200_ESTATE; }
+  if (n == 0) return COSYB200_OK;
+  DeviceGuard guard(h->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  int gs = pick_gs(h->s_max);
+  DISPATCH_GS(gs, k_ransac_score, n, n, poses, cand_labels, tmatches, TC1C2, h->aabb, h->sym, h->s_max, dists);
+  CB_LAUNCH_CHECK();
+  return COSYB200_OK;
+}
+
+int cosyb200_symmetric_distance(cosyb200_handle* h, int64_t n, const float* T1, const float* T2,
+                                const int32_t* label_ids, float* dists, int32_t* best_sym, void* stream) {
+  CB_CHECK_ARG(h != nullptr && n >= 0, "symmetric_distance: bad arguments");
+  if (!h->sym) { set_error("symmetric_distance: meshes not set"); return COSYB200_ESTATE; }
+  if (n == 0) return COSYB200_OK;
+  DeviceGuard guard(h->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  int gs = pick_gs(h->s_max);
+  DISPATCH_GS(gs, k_symmetric_distance, n, n, T1, T2, label_ids, h->aabb, h->sym, h->s_max, dists, best_sym);
+  CB_LAUNCH_CHECK();
+  return COSYB200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,102 @@
+// Shared declarations of the cosyb200 engine (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/cosyb200.h"
+
+namespace cosyb {
+
+void set_error(const char* fmt, ...);
+
+#define CB_CHECK_ARG(cond, ...)          \
+  do {                                   \
+    if (!(cond)) {                       \
+      cosyb::set_error(__VA_ARGS__);     \
+      return COSYB200_EINVAL;            \
+    }                                    \
+  } while (0)
+
+#define CB_CUDA(expr)                                                                   \
+  do {                                                                                  \
+    cudaError_t e_ = (expr);                                                            \
+    if (e_ != cudaSuccess) {                                                            \
+      cosyb::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e_)); \
+      return COSYB200_ECUDA;                                                            \
+    }                                                                                   \
+  } while (0)
+
+#define CB_LAUNCH_CHECK() CB_CUDA(cudaGetLastError())
+
+constexpr int RENDER_H = COSYB200_RENDER_H;
+constexpr int RENDER_W = COSYB200_RENDER_W;
+constexpr int N_SAMPLE = COSYB200_N_SAMPLE_POINTS;
+constexpr int IN_CH = 6;
+constexpr int N_FEATURES = 1536;
+constexpr int POSE_DIM = 9;
+constexpr float BN_EPS = 1e-3f;
+
+// One MBConv block of the trunk (see effnet_table.h).
+struct BlockSpec {
+  int k, s, e, cin, cexp, cse, cout, pad_lo, pad_hi, skip;
+  int hin, win, hout, wout;  // at the 240x320 render size
+};
+
+// Packed, BN-folded weights of one block, all on the device.
+struct BlockWeights {
+  // 1x1 convolutions are stored twice: [N][K] (K contiguous; tensor-core operand) and
+  // [K][N] (N contiguous; CUDA-core kernel operand).  BN scale is folded into the rows.
+  float* expand_nk = nullptr;   // [cexp][cin]
+  float* expand_kn = nullptr;   // [cin][cexp]
+  float* expand_bias = nullptr; // [cexp]
+  float* dw_w = nullptr;        // [k*k][cexp] tap-major, BN scale folded
+  float* dw_bias = nullptr;     // [cexp]
+  float* se_r_w = nullptr;      // [cse][cexp]
+  float* se_r_b = nullptr;      // [cse]
+  float* se_e_w = nullptr;      // [cexp][cse]
+  float* se_e_b = nullptr;      // [cexp]
+  float* proj_nk = nullptr;     // [cout][cexp]
+  float* proj_kn = nullptr;     // [cexp][cout]
+  float* proj_bias = nullptr;   // [cout]
+};
+
+struct PoseModel {
+  bool loaded = false;
+  float* stem_w = nullptr;     // [54][40]: (ky,kx,ci) major, BN scale folded
+  float* stem_bias = nullptr;  // [40]
+  std::vector<BlockWeights> blocks;
+  float* head_nk = nullptr;    // [1536][384]
+  float* head_kn = nullptr;    // [384][1536]
+  float* head_bias = nullptr;  // [1536]
+  float* fc_w = nullptr;       // [9][1536]
+  float* fc_b = nullptr;       // [9]
+  std::vector<void*> allocs;
+};
+
+}  // namespace cosyb
+
+struct cosyb200_handle {
+  int device = 0;
+  int max_batch = 0;
+  int n_sms = 148;
+  std::vector<cosyb::BlockSpec> blocks;
+  cosyb::PoseModel models[2];
+  // mesh tables
+  int n_labels = 0, s_max = 0;
+  float* pts_sampled = nullptr;  // [L][2000][3]
+  float* sym = nullptr;          // [L][s_max][4][4]
+  int32_t* n_sym = nullptr;      // [L]
+  float* aabb = nullptr;         // [L][8][3]
+  // workspaces (sized for max_batch)
+  float* act[2] = {nullptr, nullptr};  // block-boundary activations, NHWC
+  float* buf_e = nullptr;              // expanded activations / head output
+  float* buf_d = nullptr;              // depthwise output
+  float* pool_partial = nullptr;       // [B][tiles][cexp]
+  float* gate = nullptr;               // [B][cexp_max]
+  float* crops = nullptr;              // [B][3][240][320]
+  float* pose9 = nullptr;              // [B][9] scratch
+  size_t act_elems = 0, e_elems = 0, d_elems = 0, partial_elems = 0;
+};

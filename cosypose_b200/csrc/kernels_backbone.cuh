@@ -1,0 +1,370 @@
+// EfficientNet-B3 trunk kernels, fp32, NHWC activations (reference: models/efficientnet.py:71-98,
+// 174-190; BN eval eps 1e-3 folded at load; swish = x*sigmoid(x), efficientnet_utils.py:37-57).
+//   k_stem        3x3 s2 6->40 + bias + swish; reads the crop and render planes directly (the
+//                 6-channel concat of pose.py:104 never exists in memory)
+//   k_pw_gemm     1x1 convolution as a row-major GEMM on CUDA cores with fused bias / swish /
+//                 SE gate on the A operand / residual add          (expand, project, head)
+//   k_dwconv      depthwise kxk (k3/k5, s1/s2, static asymmetric "same" padding) + bias + swish,
+//                 also emits deterministic per-tile channel sums for the squeeze step
+//   k_se_gate     squeeze-excite: tile sums -> mean -> FC+swish -> FC+sigmoid -> gate[B][Cexp]
+//   k_pool_fc_update  mean pool over 7x10, Linear(1536,9), 6D->R + image-space pose update
+#pragma once
+#include "common.h"
+#include "kernels_geometry.cuh"
+
+namespace cosyb {
+
+__device__ __forceinline__ float swishf(float v) { return __fdividef(v, 1.0f + expf(-v)); }
+__device__ __forceinline__ float sigmoidf_(float v) { return __fdividef(1.0f, 1.0f + expf(-v)); }
+
+// ------------------------------------------------------------------------------------------ stem
+constexpr int STEM_TX = 32, STEM_TY = 8;                    // output tile
+constexpr int STEM_IW = 2 * STEM_TX + 1, STEM_IH = 2 * STEM_TY + 1;  // 65 x 17 input tile
+constexpr int STEM_IWP = STEM_IW + 1;                        // padded row
+constexpr int STEM_CO = 40;
+constexpr int STEM_SMEM = STEM_TX * STEM_TY * STEM_CO;       // 10240 floats, aliased for the epilogue
+static_assert(IN_CH * STEM_IH * STEM_IWP + 54 * STEM_CO <= STEM_SMEM, "stem smem");
+
+__global__ void __launch_bounds__(STEM_TX* STEM_TY)
+k_stem(const float* __restrict__ crops, const float* __restrict__ renders,
+       const float* __restrict__ w /*[54][40]*/, const float* __restrict__ bias, float* __restrict__ out) {
+  constexpr int H = RENDER_H, W = RENDER_W, HO = H / 2, WO = W / 2;
+  __shared__ __align__(16) float smem[STEM_SMEM];
+  float* s_in = smem;                                // [6][17][66]
+  float* s_w = smem + IN_CH * STEM_IH * STEM_IWP;    // [54][40]
+  const int b = blockIdx.z;
+  const int ox0 = blockIdx.x * STEM_TX, oy0 = blockIdx.y * STEM_TY;
+  const int tid = threadIdx.y * STEM_TX + threadIdx.x;
+  for (int i = tid; i < 54 * STEM_CO; i += STEM_TX * STEM_TY) s_w[i] = w[i];
+  for (int i = tid; i < IN_CH * STEM_IH * STEM_IW; i += STEM_TX * STEM_TY) {
+    int c = i / (STEM_IH * STEM_IW), r = i % (STEM_IH * STEM_IW);
+    int iy = r / STEM_IW, ix = r % STEM_IW;
+    int gy = 2 * oy0 + iy, gx = 2 * ox0 + ix;   // pad (0,1): only the high side can fall outside
+    float v = 0.f;
+    if (gy < H && gx < W) {
+      const float* src = c < 3 ? crops : renders;
+      v = __ldg(src + (((size_t)b * 3 + (c % 3)) * H + gy) * W + gx);
+    }
+    s_in[(c * STEM_IH + iy) * STEM_IWP + ix] = v;
+  }
+  __syncthreads();
+  float acc[STEM_CO];
+#pragma unroll
+  for (int i = 0; i < STEM_CO; ++i) acc[i] = 0.f;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+#pragma unroll 1
+  for (int c = 0; c < IN_CH; ++c) {
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        float v = s_in[(c * STEM_IH + 2 * ty + ky) * STEM_IWP + 2 * tx + kx];
+        const float4* wr = reinterpret_cast<const float4*>(s_w + ((ky * 3 + kx) * IN_CH + c) * STEM_CO);
+#pragma unroll
+        for (int q = 0; q < STEM_CO / 4; ++q) {
+          float4 ww = wr[q];
+          acc[4 * q + 0] = fmaf(v, ww.x, acc[4 * q + 0]);
+          acc[4 * q + 1] = fmaf(v, ww.y, acc[4 * q + 1]);
+          acc[4 * q + 2] = fmaf(v, ww.z, acc[4 * q + 2]);
+          acc[4 * q + 3] = fmaf(v, ww.w, acc[4 * q + 3]);
+        }
+      }
+    }
+  }
+  __syncthreads();  // everyone is done with s_in / s_w: reuse as the output staging tile
+  float4* s_out = reinterpret_cast<float4*>(smem);
+#pragma unroll
+  for (int q = 0; q < STEM_CO / 4; ++q) {
+    float4 o;
+    o.x = swishf(acc[4 * q + 0] + __ldg(bias + 4 * q + 0));
+    o.y = swishf(acc[4 * q + 1] + __ldg(bias + 4 * q + 1));
+    o.z = swishf(acc[4 * q + 2] + __ldg(bias + 4 * q + 2));
+    o.w = swishf(acc[4 * q + 3] + __ldg(bias + 4 * q + 3));
+    s_out[tid * (STEM_CO / 4) + q] = o;
+  }
+  __syncthreads();
+  // each tile row is STEM_TX*40 contiguous floats in the NHWC output
+  constexpr int ROW_V4 = STEM_TX * STEM_CO / 4;
+  for (int i = tid; i < STEM_TY * ROW_V4; i += STEM_TX * STEM_TY) {
+    int r = i / ROW_V4, j = i % ROW_V4;
+    float4* dst = reinterpret_cast<float4*>(out + (((size_t)b * HO + oy0 + r) * WO + ox0) * STEM_CO);
+    dst[j] = s_out[r * ROW_V4 + j];
+  }
+}
+
+// ------------------------------------------------------------------------------- pointwise GEMM
+// C[M][N] = epi( (A[M][K] (*gate[m / rows_per_img][k])) @ Wkn[K][N] + bias[N] ) (+ resid[M][N])
+// K % 4 == 0 and N % 4 == 0 (all trunk widths are multiples of 8).
+constexpr int GEMM_BK = 16;
+constexpr int GEMM_THREADS = 256;
+
+template <int BM, int BN, int TM, int TN, bool GATE, bool SWISH, bool RESID>
+__global__ void __launch_bounds__(GEMM_THREADS)
+k_pw_gemm(const float* __restrict__ A, const float* __restrict__ Wkn, const float* __restrict__ bias,
+          const float* __restrict__ gate, const float* __restrict__ resid, float* __restrict__ C,
+          int M, int N, int K, int rows_per_img) {
+  static_assert((BM / TM) * (BN / TN) == GEMM_THREADS, "thread tiling");
+  static_assert(TM % 4 == 0 && TN % 4 == 0, "float4 fragments");
+  constexpr int APAD = 4;
+  constexpr int A_V4 = BM * GEMM_BK / 4 / GEMM_THREADS;  // float4 loads of A per thread
+  constexpr int B_V4 = GEMM_BK * BN / 4;                 // float4 loads of B per CTA
+  static_assert(BM * GEMM_BK / 4 % GEMM_THREADS == 0, "A tile load");
+  __shared__ __align__(16) float As[GEMM_BK][BM + APAD];
+  __shared__ __align__(16) float Bs[GEMM_BK][BN];
+  const int tid = threadIdx.x;
+  const int tn = tid % (BN / TN), tm = tid / (BN / TN);
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  float4 a_reg[A_V4];
+  float4 b_reg[(B_V4 + GEMM_THREADS - 1) / GEMM_THREADS];
+
+  auto load_tiles = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < A_V4; ++i) {
+      int idx = tid + i * GEMM_THREADS;
+      int row = idx / (GEMM_BK / 4), kq = idx % (GEMM_BK / 4);
+      int m = m0 + row, k = k0 + kq * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (m < M && k < K) {
+        v = *reinterpret_cast<const float4*>(A + (size_t)m * K + k);
+        if (GATE) {
+          float4 g = __ldg(reinterpret_cast<const float4*>(gate + (size_t)(m / rows_per_img) * K + k));
+          v.x *= g.x; v.y *= g.y; v.z *= g.z; v.w *= g.w;
+        }
+      }
+      a_reg[i] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < (B_V4 + GEMM_THREADS - 1) / GEMM_THREADS; ++i) {
+      int idx = tid + i * GEMM_THREADS;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (idx < B_V4) {
+        int kr = idx / (BN / 4), nq = idx % (BN / 4);
+        int k = k0 + kr, n = n0 + nq * 4;
+        if (k < K && n < N) v = __ldg(reinterpret_cast<const float4*>(Wkn + (size_t)k * N + n));
+      }
+      b_reg[i] = v;
+    }
+  };
+  auto store_tiles = [&]() {
+#pragma unroll
+    for (int i = 0; i < A_V4; ++i) {
+      int idx = tid + i * GEMM_THREADS;
+      int row = idx / (GEMM_BK / 4), kq = idx % (GEMM_BK / 4);
+      As[kq * 4 + 0][row] = a_reg[i].x;
+      As[kq * 4 + 1][row] = a_reg[i].y;
+      As[kq * 4 + 2][row] = a_reg[i].z;
+      As[kq * 4 + 3][row] = a_reg[i].w;
+    }
+#pragma unroll
+    for (int i = 0; i < (B_V4 + GEMM_THREADS - 1) / GEMM_THREADS; ++i) {
+      int idx = tid + i * GEMM_THREADS;
+      if (idx < B_V4) {
+        int kr = idx / (BN / 4), nq = idx % (BN / 4);
+        *reinterpret_cast<float4*>(&Bs[kr][nq * 4]) = b_reg[i];
+      }
+    }
+  };
+
+  load_tiles(0);
+  for (int k0 = 0; k0 < K; k0 += GEMM_BK) {
+    store_tiles();
+    __syncthreads();
+    if (k0 + GEMM_BK < K) load_tiles(k0 + GEMM_BK);
+#pragma unroll
+    for (int kk = 0; kk < GEMM_BK; ++kk) {
+      float a[TM], bb[TN];
+#pragma unroll
+      for (int i = 0; i < TM / 4; ++i) {
+        float4 v = *reinterpret_cast<const float4*>(&As[kk][tm * TM + i * 4]);
+        a[i * 4 + 0] = v.x; a[i * 4 + 1] = v.y; a[i * 4 + 2] = v.z; a[i * 4 + 3] = v.w;
+      }
+#pragma unroll
+      for (int j = 0; j < TN / 4; ++j) {
+        float4 v = *reinterpret_cast<const float4*>(&Bs[kk][tn * TN + j * 4]);
+        bb[j * 4 + 0] = v.x; bb[j * 4 + 1] = v.y; bb[j * 4 + 2] = v.z; bb[j * 4 + 3] = v.w;
+      }
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    int m = m0 + tm * TM + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < TN / 4; ++j) {
+      int n = n0 + tn * TN + j * 4;
+      if (n >= N) continue;
+      float4 bv = __ldg(reinterpret_cast<const float4*>(bias + n));
+      float4 o;
+      o.x = acc[i][j * 4 + 0] + bv.x;
+      o.y = acc[i][j * 4 + 1] + bv.y;
+      o.z = acc[i][j * 4 + 2] + bv.z;
+      o.w = acc[i][j * 4 + 3] + bv.w;
+      if (SWISH) { o.x = swishf(o.x); o.y = swishf(o.y); o.z = swishf(o.z); o.w = swishf(o.w); }
+      if (RESID) {
+        float4 r = *reinterpret_cast<const float4*>(resid + (size_t)m * N + n);
+        o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+      }
+      *reinterpret_cast<float4*>(C + (size_t)m * N + n) = o;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------ depthwise
+// in [B][H][W][C] -> out [B][Ho][Wo][C]; thread = (pixel lane p, channel quad cq) with a fixed
+// channel quad, so the per-tile channel sums reduce without atomics (deterministic).
+//   grid = (tiles_per_img, n_chunks, B); block = Gc * P threads (Gc = C/4/n_chunks channel quads)
+constexpr int DW_MAX_THREADS = 256;
+
+template <int KS, int S>
+__global__ void __launch_bounds__(DW_MAX_THREADS)
+k_dwconv(const float* __restrict__ in, const float* __restrict__ w /*[KS*KS][C]*/,
+         const float* __restrict__ bias, float* __restrict__ out, float* __restrict__ partial,
+         int H, int W, int C, int Ho, int Wo, int pad_lo, int Gc, int P, int pix_per_tile,
+         int tiles_per_img) {
+  __shared__ float4 sred[DW_MAX_THREADS];
+  const int b = blockIdx.z, tile = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int cq = blockIdx.y * Gc + tid % Gc;  // channel quad
+  const int p = tid / Gc;
+  const int c = cq * 4;
+  const int npix = Ho * Wo;
+  const int pix_end = min(npix, (tile + 1) * pix_per_tile);
+  const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + c));
+  const float* inb = in + (size_t)b * H * W * C;
+  float* outb = out + (size_t)b * npix * C;
+  float4 psum = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int pix = tile * pix_per_tile + p; pix < pix_end; pix += P) {
+    const int oy = pix / Wo, ox = pix % Wo;
+    const int iy0 = oy * S - pad_lo, ix0 = ox * S - pad_lo;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int ky = 0; ky < KS; ++ky) {
+      const int iy = iy0 + ky;
+      if (iy < 0 || iy >= H) continue;
+#pragma unroll
+      for (int kx = 0; kx < KS; ++kx) {
+        const int ix = ix0 + kx;
+        if (ix < 0 || ix >= W) continue;
+        float4 v = *reinterpret_cast<const float4*>(inb + ((size_t)iy * W + ix) * C + c);
+        float4 ww = __ldg(reinterpret_cast<const float4*>(w + (size_t)(ky * KS + kx) * C + c));
+        acc.x = fmaf(v.x, ww.x, acc.x);
+        acc.y = fmaf(v.y, ww.y, acc.y);
+        acc.z = fmaf(v.z, ww.z, acc.z);
+        acc.w = fmaf(v.w, ww.w, acc.w);
+      }
+    }
+    float4 o;
+    o.x = swishf(acc.x + bv.x);
+    o.y = swishf(acc.y + bv.y);
+    o.z = swishf(acc.z + bv.z);
+    o.w = swishf(acc.w + bv.w);
+    *reinterpret_cast<float4*>(outb + (size_t)pix * C + c) = o;
+    psum.x += o.x; psum.y += o.y; psum.z += o.z; psum.w += o.w;
+  }
+  sred[tid] = psum;
+  __syncthreads();
+  if (tid < Gc) {
+    float4 s = sred[tid];
+    for (int q = 1; q < P; ++q) {
+      float4 t = sred[q * Gc + tid];
+      s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+    }
+    *reinterpret_cast<float4*>(partial + ((size_t)b * tiles_per_img + tile) * C + c) = s;
+  }
+}
+
+// -------------------------------------------------------------------------------- squeeze-excite
+// gate[b][c] = sigmoid(be[c] + sum_j We[c][j] * swish(br[j] + sum_c' Wr[j][c'] * mean[c']))
+// (reference: models/efficientnet.py:85-88).  One CTA per hypothesis.
+constexpr int SE_THREADS = 256;
+constexpr int SE_MAX_C = 2304, SE_MAX_R = 96;
+
+__global__ void __launch_bounds__(SE_THREADS)
+k_se_gate(const float* __restrict__ partial, int tiles_per_img, int C, int Cse, float inv_hw,
+          const float* __restrict__ wr, const float* __restrict__ br, const float* __restrict__ we,
+          const float* __restrict__ be, float* __restrict__ gate) {
+  __shared__ float s_mean[SE_MAX_C];
+  __shared__ float s_r[SE_MAX_R];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const float* pb = partial + (size_t)b * tiles_per_img * C;
+  for (int c = tid; c < C; c += SE_THREADS) {
+    float s = 0.f;
+    for (int t = 0; t < tiles_per_img; ++t) s += pb[(size_t)t * C + c];
+    s_mean[c] = s * inv_hw;
+  }
+  __syncthreads();
+  const int warp = tid / 32, lane = tid % 32;
+  for (int j = warp; j < Cse; j += SE_THREADS / 32) {
+    const float* wrow = wr + (size_t)j * C;
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s = fmaf(__ldg(wrow + c), s_mean[c], s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) s_r[j] = swishf(s + __ldg(br + j));
+  }
+  __syncthreads();
+  for (int c = tid; c < C; c += SE_THREADS) {
+    const float* wrow = we + (size_t)c * Cse;
+    float s = __ldg(be + c);
+    for (int j = 0; j < Cse; ++j) s = fmaf(__ldg(wrow + j), s_r[j], s);
+    gate[(size_t)b * C + c] = sigmoidf_(s);
+  }
+}
+
+// ------------------------------------------------------------------- pool + FC + pose update
+// feat [B][70][1536] (head output, swish applied) -> pose9 [B][9] -> TCO_out (optional).
+// (reference: models/pose.py:83-86 and :69-79).
+constexpr int HEAD_THREADS = 256;
+
+__global__ void __launch_bounds__(HEAD_THREADS)
+k_pool_fc_update(const float* __restrict__ feat, int n_pos, const float* __restrict__ fc_w,
+                 const float* __restrict__ fc_b, float* __restrict__ pose9,
+                 const float* __restrict__ TCO_in, const float* __restrict__ K_crop,
+                 float* __restrict__ TCO_out) {
+  __shared__ float s_pool[N_FEATURES];
+  __shared__ float s_pose[POSE_DIM];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const float* fb = feat + (size_t)b * n_pos * N_FEATURES;
+  const float inv = 1.0f / (float)n_pos;
+  for (int c = tid; c < N_FEATURES; c += HEAD_THREADS) {
+    float s = 0.f;
+    for (int p = 0; p < n_pos; ++p) s += fb[(size_t)p * N_FEATURES + c];
+    s_pool[c] = s * inv;
+  }
+  __syncthreads();
+  const int warp = tid / 32, lane = tid % 32;
+  for (int j = warp; j < POSE_DIM; j += HEAD_THREADS / 32) {
+    const float* wrow = fc_w + (size_t)j * N_FEATURES;
+    float s = 0.f;
+    for (int c = lane; c < N_FEATURES; c += 32) s = fmaf(__ldg(wrow + c), s_pool[c], s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) {
+      s += __ldg(fc_b + j);
+      s_pose[j] = s;
+      pose9[b * POSE_DIM + j] = s;
+    }
+  }
+  __syncthreads();
+  if (tid == 0 && TCO_out != nullptr) {
+    float To[16];
+    pose_update_one(TCO_in + b * 16, K_crop + b * 9, s_pose, To);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) TCO_out[b * 16 + i] = To[i];
+  }
+}
+
+}  // namespace cosyb

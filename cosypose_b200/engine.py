@@ -1,0 +1,313 @@
+"""Thin Python wrapper over one cosyb200 handle: torch tensors in, raw pointers out.
+
+PyTorch is used for device memory and streams only; every computation below is a call into
+libcosyb200.so.  Tensors must be fp32 / int32, contiguous and on the engine's CUDA device.
+"""
+import ctypes
+from ctypes import c_char_p, c_int32, c_int64, c_void_p
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import effnet_spec as spec
+
+RENDER_H, RENDER_W = spec.RENDER_H, spec.RENDER_W
+
+
+def _ptr(t):
+    return c_void_p(t.data_ptr()) if t is not None else c_void_p(None)
+
+
+def _np_ptr(a):
+    return c_void_p(a.ctypes.data) if a is not None else c_void_p(None)
+
+
+class Engine:
+    def __init__(self, device=None, max_batch=64):
+        L = _lib.lib()
+        if not torch.cuda.is_available():
+            raise _lib.EngineError('cosypose_b200 needs a CUDA device (sm_100a); there is no CPU path')
+        if device is None:
+            device = torch.cuda.current_device()
+        self.device = torch.device('cuda', device if isinstance(device, int) else torch.device(device).index or 0)
+        self.max_batch = int(max_batch)
+        h = c_void_p()
+        _lib.check(L.cosyb200_create(ctypes.byref(h), self.device.index, self.max_batch), 'create')
+        self._h = h
+        self._L = L
+        self.n_labels = 0
+        self.s_max = 0
+        self.loaded = [False, False]
+
+    def close(self):
+        if getattr(self, '_h', None):
+            self._L.cosyb200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- helpers ------------------------------------------------------------------------------
+    def _stream(self):
+        return c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _chk(self, t, dtype, shape=None, name='tensor'):
+        assert isinstance(t, torch.Tensor), f'{name} must be a tensor'
+        assert t.device == self.device, f'{name} is on {t.device}, engine on {self.device}'
+        assert t.dtype == dtype, f'{name} must be {dtype}, got {t.dtype}'
+        assert t.is_contiguous(), f'{name} must be contiguous'
+        if shape is not None:
+            assert tuple(t.shape) == tuple(shape), f'{name} has shape {tuple(t.shape)}, expected {tuple(shape)}'
+        return t
+
+    def _new(self, *shape, dtype=torch.float32):
+        return torch.empty(shape, dtype=dtype, device=self.device)
+
+    # -- setup --------------------------------------------------------------------------------
+    def load_pose_model(self, slot, state_dict):
+        """state_dict in the reference's naming; int64 counters ignored."""
+        items = [(k, v.detach().to('cpu', torch.float32).contiguous())
+                 for k, v in state_dict.items() if torch.is_floating_point(v)]
+        n = len(items)
+        names = (c_char_p * n)(*[k.encode() for k, _ in items])
+        ptrs = (c_void_p * n)(*[v.data_ptr() for _, v in items])
+        numels = (c_int64 * n)(*[v.numel() for _, v in items])
+        _lib.check(self._L.cosyb200_load_pose_model(self._h, slot, n, names, ptrs, numels), 'load_pose_model')
+        self.loaded[slot] = True
+
+    def set_meshes(self, points, symmetries, n_sym, aabb=None, point_ids=None):
+        """points [L,P,3] (or None for a matching-only engine), symmetries [L,S,4,4] identity
+        padded, n_sym [L]; aabb [L,8,3] defaults to the corners of `points`."""
+        sym = np.ascontiguousarray(symmetries.detach().cpu().numpy() if isinstance(symmetries, torch.Tensor) else symmetries, dtype=np.float32)
+        n_sym = np.ascontiguousarray(n_sym, dtype=np.int32)
+        L, S = sym.shape[:2]
+        pts = None
+        if points is not None:
+            pts = np.ascontiguousarray(points.detach().cpu().numpy() if isinstance(points, torch.Tensor) else points, dtype=np.float32)
+            assert pts.shape[0] == L and pts.shape[2] == 3
+            if point_ids is None:
+                point_ids = sample_point_ids(pts.shape[1])
+            point_ids = np.ascontiguousarray(point_ids, dtype=np.int64)
+            if aabb is None:
+                aabb = aabb_corners(pts)
+        assert aabb is not None, 'aabb is required when points is None'
+        aabb = np.ascontiguousarray(aabb.detach().cpu().numpy() if isinstance(aabb, torch.Tensor) else aabb, dtype=np.float32)
+        assert aabb.shape == (L, 8, 3)
+        _lib.check(self._L.cosyb200_set_meshes(
+            self._h, L, pts.shape[1] if pts is not None else 0, _np_ptr(pts),
+            len(point_ids) if pts is not None else 0, _np_ptr(point_ids) if pts is not None else c_void_p(None),
+            S, _np_ptr(sym), _np_ptr(n_sym), _np_ptr(aabb)), 'set_meshes')
+        self.n_labels, self.s_max = L, S
+
+    # -- single-view path ---------------------------------------------------------------------
+    def tco_init(self, boxes, K, label_ids, zup=False):
+        B = boxes.shape[0]
+        self._chk(boxes, torch.float32, (B, 4), 'boxes')
+        self._chk(K, torch.float32, (B, 3, 3), 'K')
+        self._chk(label_ids, torch.int32, (B,), 'label_ids')
+        TCO = self._new(B, 4, 4)
+        _lib.check(self._L.cosyb200_tco_init(self._h, B, int(zup), _ptr(boxes), _ptr(K), _ptr(label_ids),
+                                             _ptr(TCO), self._stream()), 'tco_init')
+        return TCO
+
+    def prepare_iter(self, K, TCO, label_ids, img_hw):
+        B = K.shape[0]
+        self._chk(K, torch.float32, (B, 3, 3), 'K')
+        self._chk(TCO, torch.float32, (B, 4, 4), 'TCO')
+        self._chk(label_ids, torch.int32, (B,), 'label_ids')
+        boxes_rend, boxes_crop, K_crop = self._new(B, 4), self._new(B, 4), self._new(B, 3, 3)
+        _lib.check(self._L.cosyb200_prepare_iter(
+            self._h, B, int(img_hw[0]), int(img_hw[1]), _ptr(K), _ptr(TCO), _ptr(label_ids),
+            _ptr(boxes_rend), _ptr(boxes_crop), _ptr(K_crop), self._stream()), 'prepare_iter')
+        return boxes_rend, boxes_crop, K_crop
+
+    def roi_crop(self, images, im_ids, boxes_crop):
+        B = boxes_crop.shape[0]
+        n_im, c, H, W = images.shape
+        assert c == 3
+        self._chk(images, torch.float32, name='images')
+        self._chk(im_ids, torch.int32, (B,), 'im_ids')
+        self._chk(boxes_crop, torch.float32, (B, 4), 'boxes_crop')
+        crops = self._new(B, 3, RENDER_H, RENDER_W)
+        _lib.check(self._L.cosyb200_roi_crop(self._h, B, _ptr(images), n_im, H, W, _ptr(im_ids),
+                                             _ptr(boxes_crop), _ptr(crops), self._stream()), 'roi_crop')
+        return crops
+
+    def net_forward(self, slot, crops, renders, taps=False):
+        B = crops.shape[0]
+        self._chk(crops, torch.float32, (B, 3, RENDER_H, RENDER_W), 'crops')
+        self._chk(renders, torch.float32, (B, 3, RENDER_H, RENDER_W), 'renders')
+        pose9 = self._new(B, 9)
+        tap_arr, tap_tensors = None, None
+        if taps:
+            shapes = spec.activation_shapes()[1:]   # stem, block0..25, head
+            tap_tensors = {name: self._new(B, h, w, c) for name, h, w, c in shapes}
+            tap_arr = (c_void_p * len(shapes))(*[tap_tensors[name].data_ptr() for name, *_ in shapes])
+        _lib.check(self._L.cosyb200_net_forward(self._h, slot, B, _ptr(crops), _ptr(renders), _ptr(pose9),
+                                                tap_arr, self._stream()), 'net_forward')
+        return (pose9, tap_tensors) if taps else pose9
+
+    def update_pose(self, TCO, K_crop, pose9):
+        B = TCO.shape[0]
+        self._chk(TCO, torch.float32, (B, 4, 4), 'TCO')
+        self._chk(K_crop, torch.float32, (B, 3, 3), 'K_crop')
+        self._chk(pose9, torch.float32, (B, 9), 'pose9')
+        out = self._new(B, 4, 4)
+        _lib.check(self._L.cosyb200_update_pose(self._h, B, _ptr(TCO), _ptr(K_crop), _ptr(pose9), _ptr(out),
+                                                self._stream()), 'update_pose')
+        return out
+
+    def refine_iter(self, slot, images, im_ids, boxes_crop, renders, K_crop, TCO):
+        B = TCO.shape[0]
+        n_im, c, H, W = images.shape
+        assert c == 3
+        self._chk(images, torch.float32, name='images')
+        self._chk(im_ids, torch.int32, (B,), 'im_ids')
+        self._chk(boxes_crop, torch.float32, (B, 4), 'boxes_crop')
+        self._chk(renders, torch.float32, (B, 3, RENDER_H, RENDER_W), 'renders')
+        self._chk(K_crop, torch.float32, (B, 3, 3), 'K_crop')
+        self._chk(TCO, torch.float32, (B, 4, 4), 'TCO')
+        pose9, TCO_out = self._new(B, 9), self._new(B, 4, 4)
+        _lib.check(self._L.cosyb200_refine_iter(
+            self._h, slot, B, _ptr(images), n_im, H, W, _ptr(im_ids), _ptr(boxes_crop), _ptr(renders),
+            _ptr(K_crop), _ptr(TCO), _ptr(pose9), _ptr(TCO_out), self._stream()), 'refine_iter')
+        return pose9, TCO_out
+
+    def refine_n(self, slot, images, im_ids, K, label_ids, renders, TCO, out=None):
+        """n_iter = renders.shape[0] iterations on pre-rendered views; returns a dict of
+        per-iteration tensors (TCO_output, K_crop, boxes_rend, boxes_crop, pose)."""
+        n_iter, B = renders.shape[:2]
+        n_im, c, H, W = images.shape
+        self._chk(images, torch.float32, name='images')
+        self._chk(im_ids, torch.int32, (B,), 'im_ids')
+        self._chk(K, torch.float32, (B, 3, 3), 'K')
+        self._chk(label_ids, torch.int32, (B,), 'label_ids')
+        self._chk(renders, torch.float32, (n_iter, B, 3, RENDER_H, RENDER_W), 'renders')
+        self._chk(TCO, torch.float32, (B, 4, 4), 'TCO')
+        if out is None:
+            out = dict(TCO_output=self._new(n_iter, B, 4, 4), K_crop=self._new(n_iter, B, 3, 3),
+                       boxes_rend=self._new(n_iter, B, 4), boxes_crop=self._new(n_iter, B, 4),
+                       pose=self._new(n_iter, B, 9))
+        _lib.check(self._L.cosyb200_refine_n(
+            self._h, slot, B, n_iter, _ptr(images), n_im, H, W, _ptr(im_ids), _ptr(K), _ptr(label_ids),
+            _ptr(renders), _ptr(TCO), _ptr(out['TCO_output']), _ptr(out['K_crop']), _ptr(out['boxes_rend']),
+            _ptr(out['boxes_crop']), _ptr(out['pose']), self._stream()), 'refine_n')
+        return out
+
+    # -- multiview ----------------------------------------------------------------------------
+    def ransac_models(self, poses, cand_label_ids, seeds):
+        n_seeds = seeds.shape[1]
+        self._chk(poses, torch.float32, name='poses')
+        self._chk(cand_label_ids, torch.int32, (poses.shape[0],), 'cand_label_ids')
+        self._chk(seeds, torch.int32, (6, n_seeds), 'seeds')
+        TC1C2 = self._new(n_seeds, 4, 4)
+        _lib.check(self._L.cosyb200_ransac_models(self._h, n_seeds, _ptr(poses), _ptr(cand_label_ids),
+                                                  _ptr(seeds), _ptr(TC1C2), self._stream()), 'ransac_models')
+        return TC1C2
+
+    def ransac_score(self, poses, cand_label_ids, tmatches, TC1C2):
+        n = tmatches.shape[1]
+        self._chk(poses, torch.float32, name='poses')
+        self._chk(cand_label_ids, torch.int32, (poses.shape[0],), 'cand_label_ids')
+        self._chk(tmatches, torch.int32, (3, n), 'tmatches')
+        self._chk(TC1C2, torch.float32, name='TC1C2')
+        dists = self._new(n)
+        _lib.check(self._L.cosyb200_ransac_score(self._h, n, _ptr(poses), _ptr(cand_label_ids), _ptr(tmatches),
+                                                 _ptr(TC1C2), _ptr(dists), self._stream()), 'ransac_score')
+        return dists
+
+    def symmetric_distance(self, T1, T2, label_ids):
+        n = T1.shape[0]
+        self._chk(T1, torch.float32, (n, 4, 4), 'T1')
+        self._chk(T2, torch.float32, (n, 4, 4), 'T2')
+        self._chk(label_ids, torch.int32, (n,), 'label_ids')
+        dists, best = self._new(n), self._new(n, dtype=torch.int32)
+        _lib.check(self._L.cosyb200_symmetric_distance(self._h, n, _ptr(T1), _ptr(T2), _ptr(label_ids),
+                                                       _ptr(dists), _ptr(best), self._stream()), 'symmetric_distance')
+        return dists, best
+
+
+# -- host-side tables ----------------------------------------------------------------------------
+
+def sample_point_ids(n_points_max, n_points=2000):
+    """The fixed subset Meshes.sample_points(2000, deterministic=True) selects
+    (reference: lib3d/mesh_ops.py:31-41): RandomState(0).choice without replacement."""
+    return np.random.RandomState(0).choice(n_points_max, size=n_points, replace=False)
+
+
+def aabb_corners(points):
+    """8 axis-aligned box corners per label in the reference's vertex order
+    (reference: lib3d/mesh_ops.py:15-28).  points [L,P,3] -> [L,8,3]."""
+    pts = np.asarray(points)
+    mn, mx = pts.min(axis=1), pts.max(axis=1)
+    sel = [(0, 1, 1), (1, 1, 1), (1, 0, 1), (0, 0, 1), (0, 1, 0), (1, 1, 0), (1, 0, 0), (0, 0, 0)]
+    out = np.empty((pts.shape[0], 8, 3), dtype=pts.dtype)
+    for i, s in enumerate(sel):
+        for a in range(3):
+            out[:, i, a] = mx[:, a] if s[a] else mn[:, a]
+    return out
+
+
+# -- host-only integer stages (no GPU needed) ------------------------------------------------------
+
+def ransac_infos(view_ids, label_ids, n_ransac_iter, seed=0):
+    L = _lib.lib()
+    v = np.ascontiguousarray(view_ids, dtype=np.int32)
+    l = np.ascontiguousarray(label_ids, dtype=np.int32)
+    assert v.shape == l.shape and v.ndim == 1
+    ns, nm = c_int64(0), c_int64(0)
+    _lib.check(L.cosyb200_ransac_infos(len(v), _np_ptr(v), _np_ptr(l), int(n_ransac_iter), int(seed),
+                                       ctypes.byref(ns), ctypes.byref(nm), None, None), 'ransac_infos')
+    seeds = np.empty((6, ns.value), dtype=np.int32)
+    tm = np.empty((3, nm.value), dtype=np.int32)
+    _lib.check(L.cosyb200_ransac_infos(len(v), _np_ptr(v), _np_ptr(l), int(n_ransac_iter), int(seed),
+                                       ctypes.byref(ns), ctypes.byref(nm), _np_ptr(seeds), _np_ptr(tm)), 'ransac_infos')
+    return seeds, tm
+
+
+def ransac_inliers(seeds_view1, seeds_view2, mtc_hyp, mtc_c1, mtc_c2, dists, dist_threshold, n_min_inliers):
+    L = _lib.lib()
+    a = [np.ascontiguousarray(x, dtype=np.int32) for x in (seeds_view1, seeds_view2, mtc_hyp, mtc_c1, mtc_c2)]
+    d = np.ascontiguousarray(dists, dtype=np.float32)
+    n_seeds, n_mtc = len(a[0]), len(a[2])
+    assert len(d) == n_mtc
+    o1 = np.empty(max(n_mtc, 1), dtype=np.int32)
+    o2 = np.empty(max(n_mtc, 1), dtype=np.int32)
+    ob = np.empty(max(n_seeds, 1), dtype=np.int32)
+    no, nb = c_int64(0), c_int64(0)
+    _lib.check(L.cosyb200_ransac_inliers(
+        n_seeds, _np_ptr(a[0]), _np_ptr(a[1]), n_mtc, _np_ptr(a[2]), _np_ptr(a[3]), _np_ptr(a[4]), _np_ptr(d),
+        float(dist_threshold), int(n_min_inliers), _np_ptr(o1), _np_ptr(o2), ctypes.byref(no), _np_ptr(ob),
+        ctypes.byref(nb)), 'ransac_inliers')
+    return dict(inlier_matches_cand1=o1[:no.value].copy(), inlier_matches_cand2=o2[:no.value].copy(),
+                best_hypotheses=ob[:nb.value].copy())
+
+
+def scatter_argmin(values, group_ids, n_groups=None):
+    L = _lib.lib()
+    v = np.ascontiguousarray(values, dtype=np.float32)
+    g = np.ascontiguousarray(group_ids, dtype=np.int32)
+    assert v.shape == g.shape
+    if n_groups is None:
+        n_groups = int(len(np.unique(g)))
+    out = np.empty(max(n_groups, 1), dtype=np.int32)
+    _lib.check(L.cosyb200_scatter_argmin(len(v), _np_ptr(v), _np_ptr(g), n_groups, _np_ptr(out)), 'scatter_argmin')
+    return out[:n_groups]
+
+
+def expand_ids_for_symmetry(label_ids, n_sym_per_label):
+    L = _lib.lib()
+    l = np.ascontiguousarray(label_ids, dtype=np.int32)
+    ns = np.ascontiguousarray(n_sym_per_label, dtype=np.int32)
+    n = c_int64(0)
+    _lib.check(L.cosyb200_expand_ids_for_symmetry(len(l), _np_ptr(l), _np_ptr(ns), ctypes.byref(n), None, None),
+               'expand_ids_for_symmetry')
+    ids = np.empty(max(n.value, 1), dtype=np.int32)
+    sym = np.empty(max(n.value, 1), dtype=np.int32)
+    _lib.check(L.cosyb200_expand_ids_for_symmetry(len(l), _np_ptr(l), _np_ptr(ns), ctypes.byref(n),
+                                                  _np_ptr(ids), _np_ptr(sym)), 'expand_ids_for_symmetry')
+    return ids[:n.value], sym[:n.value]

@@ -1,0 +1,62 @@
+"""Pre-rendered views standing in for the renderer side input.
+
+The path treats the rendered view as an input (reference renderer contract:
+cosypose/models/pose.py:100-102 calling cosypose/rendering/bullet_batch_renderer.py:46-90, which
+returns float [B,3,240,320] in [0,1]).  `PreRenderedViews` replays stacks generated up front, in
+the order `CoarseRefinePosePredictor` asks for them: per stage, per chunk of `bsz_objects`
+hypotheses, per iteration.
+"""
+import torch
+
+
+class PreRenderedViews:
+    def __init__(self, stages, bsz_objects=64, device=None):
+        """stages: list of tensors [n_iter_s, N, 3, 240, 320], one per stage in call order
+        (e.g. [coarse_views, refiner_views])."""
+        self.bsz = bsz_objects
+        self.chunks = []      # flat list of [n_iter, Bc, 3, H, W] contiguous tensors, call order
+        for views in stages:
+            n = views.shape[1]
+            for s in range(0, n, bsz_objects):
+                c = views[:, s:s + bsz_objects].contiguous()
+                self.chunks.append(c.to(device) if device is not None else c)
+        self.reset()
+
+    def reset(self):
+        self._chunk = 0
+        self._it = 0
+
+    def _advance(self, n_iter_taken):
+        self._it += n_iter_taken
+        if self._it >= self.chunks[self._chunk].shape[0]:
+            self._it = 0
+            self._chunk = (self._chunk + 1) % len(self.chunks)
+
+    def prerendered(self, n_iterations, batch_size):
+        """All views of the next `n_iterations` calls as one [n_iterations, B, 3, H, W] stack."""
+        c = self.chunks[self._chunk]
+        assert self._it == 0 and c.shape[0] == n_iterations and c.shape[1] == batch_size, \
+            'pre-rendered stack does not match the call sequence'
+        self._advance(n_iterations)
+        return c
+
+    def render(self, obj_infos, TCO, K, resolution=(240, 320), **kwargs):
+        c = self.chunks[self._chunk]
+        assert c.shape[1] == len(obj_infos), 'pre-rendered stack does not match the call sequence'
+        out = c[self._it]
+        self._advance(1)
+        return out
+
+
+class PerCallRenderer:
+    """Wraps PreRenderedViews but hides `prerendered`, forcing the two-phase per-iteration path
+    (prepare_iter -> render -> refine_iter) a real renderer needs."""
+
+    def __init__(self, views):
+        self.views = views
+
+    def reset(self):
+        self.views.reset()
+
+    def render(self, *args, **kwargs):
+        return self.views.render(*args, **kwargs)

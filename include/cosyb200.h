@@ -1,0 +1,184 @@
+/*
+ * cosyb200 - C-ABI of the B200 render-and-compare refinement + multiview matching engine.
+ *
+ * The reference (ylabbe/cosypose) has no FFI registry for this path: its boundary is the
+ * Python class API (cosypose/integrated/pose_predictor.py, multiview_predictor.py) plus one
+ * pybind11 module (cosypose/csrc/cosypose_cext.cpp:264-269).  Every entry point below names the
+ * reference interface it replaces.  Conventions:
+ *   - plain pointers and sizes only; no torch / pybind types cross this boundary;
+ *   - every function returns 0 on success and a negative COSYB200_E* code on failure;
+ *     cosyb200_last_error() returns a thread-local message for the last failure;
+ *   - pointers named *_dev are device pointers on the handle's device, owned by the caller;
+ *     pointers named *_host are host pointers; all floating point is IEEE fp32, row-major;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).  Kernels are only
+ *     enqueued; nothing synchronises unless the output is a host array;
+ *   - a handle is bound to one device, owns packed weights / mesh tables / workspaces and is
+ *     not thread-safe; distinct handles may be used concurrently.
+ */
+#ifndef COSYB200_H_
+#define COSYB200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define COSYB200_OK 0
+#define COSYB200_EINVAL (-1)   /* bad argument (the Python shim raises AssertionError / ValueError) */
+#define COSYB200_ECUDA (-2)    /* CUDA runtime error */
+#define COSYB200_ESTATE (-3)   /* model / meshes not loaded */
+#define COSYB200_ENOMEM (-4)
+
+#define COSYB200_SLOT_COARSE 0
+#define COSYB200_SLOT_REFINER 1
+
+#define COSYB200_RENDER_H 240
+#define COSYB200_RENDER_W 320
+#define COSYB200_N_SAMPLE_POINTS 2000
+
+typedef struct cosyb200_handle cosyb200_handle;
+
+const char* cosyb200_last_error(void);
+int cosyb200_version(void);
+
+/* Engine lifetime.  `max_batch` bounds the number of hypotheses per call (the reference chunks
+ * at bsz_objects=64, pose_predictor.py:18,34); workspaces are allocated once here. */
+int cosyb200_create(cosyb200_handle** out, int device, int max_batch);
+int cosyb200_destroy(cosyb200_handle* h);
+
+/* EfficientNet-B3 block table compiled into the engine: out[11] = k,s,e,cin,cexp,cse,cout,
+ * pad_lo,pad_hi,skip,n_blocks (reference: models/efficientnet_utils.py:59-81,123-146,259-264). */
+int cosyb200_effnet_block(int idx, int32_t* out11);
+
+/* Replaces PosePredictor.load_state_dict (reference: models/pose.py:18-36, weights named as in
+ * SURVEY.md section 5).  `names[i]` is a state_dict key, `ptrs_host[i]` its fp32 data, `numels[i]`
+ * its element count.  BatchNorm (eps 1e-3) is folded into the conv weights here. */
+int cosyb200_load_pose_model(cosyb200_handle* h, int slot, int n_tensors,
+                             const char* const* names, const float* const* ptrs_host,
+                             const int64_t* numels);
+
+/* Replaces BatchedMeshes (reference: lib3d/rigid_mesh_database.py:59-79) + the deterministic
+ * 2000-point subset of Meshes.sample_points (lib3d/mesh_ops.py:31-41).
+ *   points_host [n_labels, n_points, 3]; point_ids_host [n_sample] (the RandomState(0) subset);
+ *   sym_host [n_labels, s_max, 4, 4] identity padded; n_sym_host [n_labels];
+ *   aabb_host [n_labels, 8, 3] (lib3d/mesh_ops.py:15-28) - the points RANSAC scoring uses. */
+int cosyb200_set_meshes(cosyb200_handle* h, int n_labels, int n_points, const float* points_host,
+                        int n_sample, const int64_t* point_ids_host, int s_max,
+                        const float* sym_host, const int32_t* n_sym_host, const float* aabb_host);
+
+/* TCO_init_from_boxes(z_range=(1,1)) (reference: lib3d/cosypose_ops.py:121-135) when zup == 0,
+ * TCO_init_from_boxes_zup_autodepth (cosypose_ops.py:138-173) when zup == 1.
+ *   boxes_dev [B,4], K_dev [B,3,3] (per hypothesis), label_ids_dev [B] -> TCO_dev [B,4,4]. */
+int cosyb200_tco_init(cosyb200_handle* h, int B, int zup, const float* boxes_dev,
+                      const float* K_dev, const int32_t* label_ids_dev, float* TCO_dev,
+                      void* stream);
+
+/* Phase A of one iteration = PosePredictor.crop_inputs without the pixel crop
+ * (reference: models/pose.py:45-67 -> lib3d/camera_geometry.py:18-87, lib3d/cropping.py:7-47).
+ *   K_dev [B,3,3] per hypothesis, TCO_dev [B,4,4], label_ids_dev [B]
+ *   -> boxes_rend_dev [B,4], boxes_crop_dev [B,4], K_crop_dev [B,3,3].
+ * The host may then call renderer.render(obj_infos, TCO, K_crop) exactly as pose.py:100-102. */
+int cosyb200_prepare_iter(cosyb200_handle* h, int B, int img_h, int img_w, const float* K_dev,
+                          const float* TCO_dev, const int32_t* label_ids_dev,
+                          float* boxes_rend_dev, float* boxes_crop_dev, float* K_crop_dev,
+                          void* stream);
+
+/* The RoI crop alone (reference: lib3d/cropping.py:74, torchvision.ops.roi_align with
+ * output (240,320), spatial_scale 1, sampling_ratio 4, aligned False).
+ *   images_dev [n_images,3,img_h,img_w] NCHW, im_ids_dev [B], boxes_crop_dev [B,4]
+ *   -> crops_dev [B,3,240,320] NCHW. */
+int cosyb200_roi_crop(cosyb200_handle* h, int B, const float* images_dev, int n_images, int img_h,
+                      int img_w, const int32_t* im_ids_dev, const float* boxes_crop_dev,
+                      float* crops_dev, void* stream);
+
+/* PosePredictor.net_forward on an explicit 6-channel input (reference: models/pose.py:81-87,
+ * models/efficientnet.py:174-190).  crops_dev / renders_dev [B,3,240,320] NCHW are channels
+ * 0-2 / 3-5 of the concatenated input (pose.py:104) -> pose9_dev [B,9].
+ * `taps_dev` (may be NULL) is an array of 28 device pointers (stem, block0..25, head) that
+ * receive the block-boundary activations in NHWC; NULL entries are skipped. */
+int cosyb200_net_forward(cosyb200_handle* h, int slot, int B, const float* crops_dev,
+                         const float* renders_dev, float* pose9_dev, float* const* taps_dev,
+                         void* stream);
+
+/* PosePredictor.update_pose, pose_dim 9 (reference: models/pose.py:69-79, lib3d/rotations.py:6-21,
+ * lib3d/cosypose_ops.py:10-31).  TCO_in [B,4,4], K_crop [B,3,3], pose9 [B,9] -> TCO_out [B,4,4]. */
+int cosyb200_update_pose(cosyb200_handle* h, int B, const float* TCO_in_dev,
+                         const float* K_crop_dev, const float* pose9_dev, float* TCO_out_dev,
+                         void* stream);
+
+/* Phase B of one iteration: crop + concat + backbone + head + pose update
+ * (reference: models/pose.py:99-108 minus the renderer call).  Images are gathered through
+ * im_ids_dev instead of being copied per hypothesis (pose_predictor.py:41). */
+int cosyb200_refine_iter(cosyb200_handle* h, int slot, int B, const float* images_dev,
+                         int n_images, int img_h, int img_w, const int32_t* im_ids_dev,
+                         const float* boxes_crop_dev, const float* renders_dev,
+                         const float* K_crop_dev, const float* TCO_in_dev, float* pose9_dev,
+                         float* TCO_out_dev, void* stream);
+
+/* PosePredictor.forward with pre-rendered views (reference: models/pose.py:89-132): n_iter
+ * iterations without returning to the host.  renders_dev [n_iter,B,3,240,320]; K_dev [B,3,3];
+ * outputs are per iteration: TCO_out [n_iter,B,4,4], K_crop [n_iter,B,3,3], boxes_rend and
+ * boxes_crop [n_iter,B,4], pose9 [n_iter,B,9]; iteration n reads TCO_out[n-1] (TCO_in_dev for n=0). */
+int cosyb200_refine_n(cosyb200_handle* h, int slot, int B, int n_iter, const float* images_dev,
+                      int n_images, int img_h, int img_w, const int32_t* im_ids_dev,
+                      const float* K_dev, const int32_t* label_ids_dev, const float* renders_dev,
+                      const float* TCO_in_dev, float* TCO_out_dev, float* K_crop_dev,
+                      float* boxes_rend_dev, float* boxes_crop_dev, float* pose9_dev, void* stream);
+
+/* ---- multiview candidate matching (reference: multiview/ransac.py:137-199) ---- */
+
+/* cosypose_cext.make_ransac_infos (reference: csrc/cosypose_cext.cpp:36-105).  Labels are dense
+ * ids (label equality is all the reference uses).  Two calls: with seeds_host == NULL it only
+ * counts; then the caller allocates and calls again.
+ *   seeds_host [6, n_seeds] rows: view1, view2, match1_cand1, match1_cand2, match2_cand1,
+ *   match2_cand2;  tmatches_host [3, n_tmatches] rows: hypothesis_id, cand1, cand2. */
+int cosyb200_ransac_infos(int n_cand, const int32_t* view_ids_host, const int32_t* label_ids_host,
+                          int n_ransac_iter, int seed, int64_t* n_seeds, int64_t* n_tmatches,
+                          int32_t* seeds_host, int32_t* tmatches_host);
+
+/* estimate_camera_poses over all seeds (reference: multiview/ransac.py:19-64).
+ *   poses_dev [n_cand,4,4], cand_label_ids_dev [n_cand], seeds_dev [6,n_seeds] (layout above)
+ *   -> TC1C2_dev [n_seeds,4,4]. */
+int cosyb200_ransac_models(cosyb200_handle* h, int64_t n_seeds, const float* poses_dev,
+                           const int32_t* cand_label_ids_dev, const int32_t* seeds_dev,
+                           float* TC1C2_dev, void* stream);
+
+/* score_tmatches over all rows (reference: multiview/ransac.py:67-88).
+ *   tmatches_dev [3,n_tmatches], TC1C2_dev [n_seeds,4,4] -> dists_dev [n_tmatches]. */
+int cosyb200_ransac_score(cosyb200_handle* h, int64_t n_tmatches, const float* poses_dev,
+                          const int32_t* cand_label_ids_dev, const int32_t* tmatches_dev,
+                          const float* TC1C2_dev, float* dists_dev, void* stream);
+
+/* symmetric_distance_batched_fast (reference: lib3d/symmetric_distances.py:38-57) on the AABB
+ * points: T1_dev, T2_dev [n,4,4], label_ids_dev [n] -> dists_dev [n], best_sym_dev [n] (may be NULL). */
+int cosyb200_symmetric_distance(cosyb200_handle* h, int64_t n, const float* T1_dev,
+                                const float* T2_dev, const int32_t* label_ids_dev,
+                                float* dists_dev, int32_t* best_sym_dev, void* stream);
+
+/* cosypose_cext.find_ransac_inliers (reference: csrc/cosypose_cext.cpp:107-216).  Outputs are
+ * written into caller buffers of capacity n_tmatches (matches) / n_seeds (best hypotheses);
+ * the counts come back through n_inlier_matches / n_best. */
+int cosyb200_ransac_inliers(int64_t n_seeds, const int32_t* seeds_view1_host,
+                            const int32_t* seeds_view2_host, int64_t n_tmatches,
+                            const int32_t* mtc_hypothesis_id_host, const int32_t* mtc_cand1_host,
+                            const int32_t* mtc_cand2_host, const float* dists_host,
+                            float dist_threshold, int n_min_inliers, int32_t* inlier_cand1_host,
+                            int32_t* inlier_cand2_host, int64_t* n_inlier_matches,
+                            int32_t* best_hypotheses_host, int64_t* n_best);
+
+/* cosypose_cext.scatter_argmin (reference: csrc/cosypose_cext.cpp:218-245): first minimum per
+ * group; out_host has one entry per group id 0..n_groups-1. */
+int cosyb200_scatter_argmin(int64_t n, const float* values_host, const int32_t* group_ids_host,
+                            int64_t n_groups, int32_t* out_host);
+
+/* cosypose_cext.expand_ids_for_symmetry (reference: csrc/cosypose_cext.cpp:247-259) over dense
+ * label ids; returns the expanded length through n_out (call with ids_expand_host == NULL to count). */
+int cosyb200_expand_ids_for_symmetry(int64_t n, const int32_t* label_ids_host,
+                                     const int32_t* n_sym_per_label_host, int64_t* n_out,
+                                     int32_t* ids_expand_host, int32_t* sym_ids_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COSYB200_H_ */
