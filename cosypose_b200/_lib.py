@@ -33,9 +33,11 @@ _SIGS = {
     'cosyb200_roi_crop': ([_P, c_int, _P, c_int, c_int, c_int, _P, _P, _P, _P], c_int),
     'cosyb200_net_forward': ([_P, c_int, c_int, _P, _P, _P, POINTER(c_void_p), _P], c_int),
     'cosyb200_update_pose': ([_P, c_int, _P, _P, _P, _P, _P], c_int),
-    'cosyb200_refine_iter': ([_P, c_int, c_int, _P, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P], c_int),
-    'cosyb200_refine_n': ([_P, c_int, c_int, c_int, _P, c_int, c_int, c_int, _P, _P, _P, _P, _P,
+    'cosyb200_refine_iter': ([_P, c_int, c_int, _P, c_int, c_int, c_int, _P, _P, _P, c_int, _P, _P, _P, _P, _P], c_int),
+    'cosyb200_refine_n': ([_P, c_int, c_int, c_int, _P, c_int, c_int, c_int, _P, _P, _P, _P, c_int, _P,
                            _P, _P, _P, _P, _P, _P], c_int),
+    'cosyb200_profile_enable': ([_P, c_int], c_int),
+    'cosyb200_profile_read': ([_P, c_int, _P, _P], c_int),
     'cosyb200_ransac_infos': ([c_int, _P, _P, c_int, c_int, POINTER(c_int64), POINTER(c_int64), _P, _P], c_int),
     'cosyb200_ransac_models': ([_P, c_int64, _P, _P, _P, _P, _P], c_int),
     'cosyb200_ransac_score': ([_P, c_int64, _P, _P, _P, _P, _P, _P], c_int),

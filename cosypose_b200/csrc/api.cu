@@ -35,6 +35,18 @@ struct DeviceGuard {
   }
 };
 
+int prof_resolve(cosyb200_handle* h) {
+  if (h->ev_cat.empty()) return 0;
+  CB_CUDA(cudaEventSynchronize(h->ev_pool[(h->ev_cat.size() - 1) * 2 + 1]));
+  for (size_t i = 0; i < h->ev_cat.size(); ++i) {
+    float ms = 0.f;
+    CB_CUDA(cudaEventElapsedTime(&ms, h->ev_pool[2 * i], h->ev_pool[2 * i + 1]));
+    h->cat_ms[h->ev_cat[i]] += ms;
+  }
+  h->ev_cat.clear();
+  return 0;
+}
+
 static int dev_alloc(void** p, size_t bytes) {
   CB_CUDA(cudaMalloc(p, bytes ? bytes : 16));
   return 0;
@@ -87,9 +99,24 @@ static void launch_gemm(bool gate, bool swish, bool resid, const float* A, const
 }
 
 // ---- depthwise dispatch ---------------------------------------------------------------------
-struct DwPlan { int n_chunks, Gc, P, pix_per_tile, tiles; };
+struct DwPlan { int n_chunks, Gc, P, pix_per_tile, tiles; int V, TH, tiles_x; bool rolling; };
 static DwPlan dw_plan(const BlockSpec& b) {
   DwPlan p;
+  p.rolling = b.s == 1;
+  if (p.rolling) {   // k_dwconv_s1: thread = (channel vector, output column), rolls down TH rows
+    p.V = b.k == 3 ? 4 : 2;
+    int G = b.cexp / p.V;
+    p.n_chunks = (G + DW_MAX_THREADS - 1) / DW_MAX_THREADS;
+    while (G % p.n_chunks) ++p.n_chunks;
+    p.Gc = G / p.n_chunks;
+    p.P = DW_MAX_THREADS / p.Gc;
+    p.TH = std::min(b.hout, 30);
+    p.tiles_x = (b.wout + p.P - 1) / p.P;
+    p.tiles = p.tiles_x * ((b.hout + p.TH - 1) / p.TH);
+    p.pix_per_tile = p.P * p.TH;
+    return p;
+  }
+  p.V = 4; p.TH = 0; p.tiles_x = 0;
   int G = b.cexp / 4;
   p.n_chunks = (G + DW_MAX_THREADS - 1) / DW_MAX_THREADS;
   while (G % p.n_chunks) ++p.n_chunks;
@@ -105,6 +132,15 @@ static int launch_dw(const BlockSpec& b, const BlockWeights& w, const float* in,
   DwPlan p = dw_plan(b);
   dim3 grid(p.tiles, p.n_chunks, B);
   int threads = p.Gc * p.P;
+  if (p.rolling) {
+#define DW1_ARGS in, w.dw_w, w.dw_bias, out, partial, b.hin, b.win, b.cexp, b.pad_lo, p.Gc, p.P, p.TH, p.tiles_x, p.tiles
+    if (b.k == 3) k_dwconv_s1<3, 4><<<grid, threads, 0, st>>>(DW1_ARGS);
+    else if (b.k == 5) k_dwconv_s1<5, 2><<<grid, threads, 0, st>>>(DW1_ARGS);
+    else { set_error("unsupported depthwise k=%d", b.k); return COSYB200_EINVAL; }
+#undef DW1_ARGS
+    CB_LAUNCH_CHECK();
+    return 0;
+  }
 #define DW_ARGS in, w.dw_w, w.dw_bias, out, partial, b.hin, b.win, b.cexp, b.hout, b.wout, b.pad_lo, p.Gc, p.P, p.pix_per_tile, p.tiles
   if (b.k == 3 && b.s == 1) k_dwconv<3, 1><<<grid, threads, 0, st>>>(DW_ARGS);
   else if (b.k == 3 && b.s == 2) k_dwconv<3, 2><<<grid, threads, 0, st>>>(DW_ARGS);
@@ -117,13 +153,15 @@ static int launch_dw(const BlockSpec& b, const BlockWeights& w, const float* in,
 }
 
 // ---- trunk forward --------------------------------------------------------------------------
-static int net_forward(cosyb200_handle* h, int slot, int B, const float* crops, const float* renders,
-                       float* pose9, float* const* taps, const float* TCO_in, const float* K_crop,
+static int net_forward(cosyb200_handle* h, int slot, int B, const float* crops, const void* renders,
+                       int render_u8, float* pose9, float* const* taps, const float* TCO_in, const float* K_crop,
                        float* TCO_out, cudaStream_t st) {
   const PoseModel& m = h->models[slot];
   {
     dim3 grid(RENDER_W / 2 / STEM_TX, RENDER_H / 2 / STEM_TY, B), block(STEM_TX, STEM_TY);
-    k_stem<<<grid, block, 0, st>>>(crops, renders, m.stem_w, m.stem_bias, h->act[0]);
+    LaunchScope ls(h, CAT_STEM, st);
+    if (render_u8) k_stem<true><<<grid, block, 0, st>>>(crops, renders, m.stem_w, m.stem_bias, h->act[0]);
+    else k_stem<false><<<grid, block, 0, st>>>(crops, renders, m.stem_w, m.stem_bias, h->act[0]);
     CB_LAUNCH_CHECK();
   }
   int cur = 0;
@@ -141,20 +179,30 @@ static int net_forward(cosyb200_handle* h, int slot, int B, const float* crops, 
     const int Min = B * b.hin * b.win, Mout = B * b.hout * b.wout;
     const float* dw_in = x;
     if (b.e != 1) {
+      LaunchScope ls(h, CAT_EXPAND, st);
       launch_gemm(false, true, false, x, w.expand_kn, w.expand_bias, nullptr, nullptr, h->buf_e, Min,
                   b.cexp, b.cin, 1, st);
       CB_LAUNCH_CHECK();
       dw_in = h->buf_e;
     }
-    rc = launch_dw(b, w, dw_in, h->buf_d, h->pool_partial, B, st);
+    {
+      LaunchScope ls(h, CAT_DW, st);
+      rc = launch_dw(b, w, dw_in, h->buf_d, h->pool_partial, B, st);
+    }
     if (rc) return rc;
     DwPlan p = dw_plan(b);
-    k_se_gate<<<B, SE_THREADS, 0, st>>>(h->pool_partial, p.tiles, b.cexp, b.cse,
-                                        1.0f / float(b.hout * b.wout), w.se_r_w, w.se_r_b, w.se_e_w,
-                                        w.se_e_b, h->gate);
+    {
+      LaunchScope ls(h, CAT_SE, st);
+      k_se_gate<<<B, SE_THREADS, 0, st>>>(h->pool_partial, p.tiles, b.cexp, b.cse,
+                                          1.0f / float(b.hout * b.wout), w.se_r_w, w.se_r_b, w.se_e_w,
+                                          w.se_e_b, h->gate);
+    }
     CB_LAUNCH_CHECK();
-    launch_gemm(true, false, b.skip != 0, h->buf_d, w.proj_kn, w.proj_bias, h->gate, x, y, Mout, b.cout,
-                b.cexp, b.hout * b.wout, st);
+    {
+      LaunchScope ls(h, CAT_PROJECT, st);
+      launch_gemm(true, false, b.skip != 0, h->buf_d, w.proj_kn, w.proj_bias, h->gate, x, y, Mout, b.cout,
+                  b.cexp, b.hout * b.wout, st);
+    }
     CB_LAUNCH_CHECK();
     cur ^= 1;
     rc = tap(1 + (int)i, y, (size_t)Mout * b.cout);
@@ -162,12 +210,18 @@ static int net_forward(cosyb200_handle* h, int slot, int B, const float* crops, 
   }
   const BlockSpec& last = h->blocks.back();
   const int n_pos = last.hout * last.wout;
-  launch_gemm(false, true, false, h->act[cur], m.head_kn, m.head_bias, nullptr, nullptr, h->buf_e,
-              B * n_pos, N_FEATURES, last.cout, 1, st);
+  {
+    LaunchScope ls(h, CAT_HEAD, st);
+    launch_gemm(false, true, false, h->act[cur], m.head_kn, m.head_bias, nullptr, nullptr, h->buf_e,
+                B * n_pos, N_FEATURES, last.cout, 1, st);
+  }
   CB_LAUNCH_CHECK();
   rc = tap(1 + (int)h->blocks.size(), h->buf_e, (size_t)B * n_pos * N_FEATURES);
   if (rc) return rc;
-  k_pool_fc_update<<<B, HEAD_THREADS, 0, st>>>(h->buf_e, n_pos, m.fc_w, m.fc_b, pose9, TCO_in, K_crop, TCO_out);
+  {
+    LaunchScope ls(h, CAT_POOL_FC, st);
+    k_pool_fc_update<<<B, HEAD_THREADS, 0, st>>>(h->buf_e, n_pos, m.fc_w, m.fc_b, pose9, TCO_in, K_crop, TCO_out);
+  }
   CB_LAUNCH_CHECK();
   return 0;
 }
@@ -242,6 +296,7 @@ int cosyb200_destroy(cosyb200_handle* h) {
   DeviceGuard guard(h->device);
   free_model(h->models[0]);
   free_model(h->models[1]);
+  for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   void* ptrs[] = {h->act[0], h->act[1], h->buf_e, h->buf_d, h->pool_partial, h->gate, h->crops, h->pose9,
                   h->pts_sampled, h->sym, h->n_sym, h->aabb};
   for (void* p : ptrs) if (p) cudaFree(p);
@@ -425,9 +480,10 @@ int cosyb200_set_meshes(cosyb200_handle* h, int n_labels, int n_points, const fl
 
 int cosyb200_tco_init(cosyb200_handle* h, int B, int zup, const float* boxes, const float* K,
                       const int32_t* label_ids, float* TCO, void* stream) {
-  if (int rc = check_batch(h, B, "tco_init")) return rc;
+  CB_CHECK_ARG(h != nullptr && B >= 1, "tco_init: bad arguments");
   if (zup) { if (!h->pts_sampled) { set_error("tco_init: meshes not set"); return COSYB200_ESTATE; } }
   DeviceGuard guard(h->device);
+  LaunchScope ls(h, CAT_GEOMETRY, (cudaStream_t)stream);
   k_tco_init<<<B, GEO_THREADS, 0, (cudaStream_t)stream>>>(B, zup, boxes, K, label_ids, h->pts_sampled, N_SAMPLE, TCO);
   CB_LAUNCH_CHECK();
   return COSYB200_OK;
@@ -436,21 +492,25 @@ int cosyb200_tco_init(cosyb200_handle* h, int B, int zup, const float* boxes, co
 int cosyb200_prepare_iter(cosyb200_handle* h, int B, int img_h, int img_w, const float* K,
                           const float* TCO, const int32_t* label_ids, float* boxes_rend,
                           float* boxes_crop, float* K_crop, void* stream) {
-  if (int rc = check_batch(h, B, "prepare_iter")) return rc;
+  CB_CHECK_ARG(h != nullptr && B >= 1, "prepare_iter: bad arguments");
   if (!h->pts_sampled) { set_error("prepare_iter: meshes not set"); return COSYB200_ESTATE; }
   CB_CHECK_ARG(img_h > 0 && img_w > 0, "prepare_iter: image size");
   DeviceGuard guard(h->device);
   float aspect = (float)((double)std::max(img_h, img_w) / (double)std::min(img_h, img_w));
+  LaunchScope ls(h, CAT_GEOMETRY, (cudaStream_t)stream);
   k_project_boxes<<<B, GEO_THREADS, 0, (cudaStream_t)stream>>>(B, K, TCO, label_ids, h->pts_sampled, N_SAMPLE,
                                                               aspect, boxes_rend, boxes_crop, K_crop);
   CB_LAUNCH_CHECK();
   return COSYB200_OK;
 }
 
-static int launch_crop(int B, const float* images, int n_images, int img_h, int img_w,
+static int launch_crop(cosyb200_handle* h, int B, const float* images, int n_images, int img_h, int img_w,
                        const int32_t* im_ids, const float* boxes_crop, float* crops, cudaStream_t st) {
   dim3 grid((RENDER_W + CROP_TX - 1) / CROP_TX, (RENDER_H + CROP_TY - 1) / CROP_TY, B), block(CROP_TX, CROP_TY);
-  k_roi_crop<<<grid, block, 0, st>>>(B, images, n_images, img_h, img_w, im_ids, boxes_crop, crops);
+  {
+    LaunchScope ls(h, CAT_CROP, st);
+    k_roi_crop<<<grid, block, 0, st>>>(B, images, n_images, img_h, img_w, im_ids, boxes_crop, crops);
+  }
   CB_LAUNCH_CHECK();
   return 0;
 }
@@ -461,7 +521,7 @@ int cosyb200_roi_crop(cosyb200_handle* h, int B, const float* images, int n_imag
   CB_CHECK_ARG(h != nullptr && B >= 1, "roi_crop: bad arguments");
   CB_CHECK_ARG(n_images >= 1 && img_h >= 2 && img_w >= 2, "roi_crop: image size");
   DeviceGuard guard(h->device);
-  return launch_crop(B, images, n_images, img_h, img_w, im_ids, boxes_crop, crops, (cudaStream_t)stream);
+  return launch_crop(h, B, images, n_images, img_h, img_w, im_ids, boxes_crop, crops, (cudaStream_t)stream);
 }
 
 int cosyb200_net_forward(cosyb200_handle* h, int slot, int B, const float* crops, const float* renders,
@@ -470,13 +530,14 @@ int cosyb200_net_forward(cosyb200_handle* h, int slot, int B, const float* crops
   CB_CHECK_ARG(slot == 0 || slot == 1, "net_forward: slot %d", slot);
   if (!h->models[slot].loaded) { set_error("net_forward: model slot %d not loaded", slot); return COSYB200_ESTATE; }
   DeviceGuard guard(h->device);
-  return net_forward(h, slot, B, crops, renders, pose9, taps, nullptr, nullptr, nullptr, (cudaStream_t)stream);
+  return net_forward(h, slot, B, crops, renders, 0, pose9, taps, nullptr, nullptr, nullptr, (cudaStream_t)stream);
 }
 
 int cosyb200_update_pose(cosyb200_handle* h, int B, const float* TCO_in, const float* K_crop,
                          const float* pose9, float* TCO_out, void* stream) {
   CB_CHECK_ARG(h != nullptr && B >= 1, "update_pose: bad arguments");
   DeviceGuard guard(h->device);
+  LaunchScope ls(h, CAT_GEOMETRY, (cudaStream_t)stream);
   k_update_pose<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(B, TCO_in, K_crop, pose9, TCO_out);
   CB_LAUNCH_CHECK();
   return COSYB200_OK;
@@ -484,20 +545,20 @@ int cosyb200_update_pose(cosyb200_handle* h, int B, const float* TCO_in, const f
 
 int cosyb200_refine_iter(cosyb200_handle* h, int slot, int B, const float* images, int n_images,
                          int img_h, int img_w, const int32_t* im_ids, const float* boxes_crop,
-                         const float* renders, const float* K_crop, const float* TCO_in, float* pose9,
-                         float* TCO_out, void* stream) {
+                         const void* renders, int render_u8, const float* K_crop, const float* TCO_in,
+                         float* pose9, float* TCO_out, void* stream) {
   if (int rc = check_batch(h, B, "refine_iter")) return rc;
   CB_CHECK_ARG(slot == 0 || slot == 1, "refine_iter: slot %d", slot);
   if (!h->models[slot].loaded) { set_error("refine_iter: model slot %d not loaded", slot); return COSYB200_ESTATE; }
   DeviceGuard guard(h->device);
   cudaStream_t st = (cudaStream_t)stream;
-  if (int rc = launch_crop(B, images, n_images, img_h, img_w, im_ids, boxes_crop, h->crops, st)) return rc;
-  return net_forward(h, slot, B, h->crops, renders, pose9 ? pose9 : h->pose9, nullptr, TCO_in, K_crop, TCO_out, st);
+  if (int rc = launch_crop(h, B, images, n_images, img_h, img_w, im_ids, boxes_crop, h->crops, st)) return rc;
+  return net_forward(h, slot, B, h->crops, renders, render_u8, pose9 ? pose9 : h->pose9, nullptr, TCO_in, K_crop, TCO_out, st);
 }
 
 int cosyb200_refine_n(cosyb200_handle* h, int slot, int B, int n_iter, const float* images,
                       int n_images, int img_h, int img_w, const int32_t* im_ids, const float* K,
-                      const int32_t* label_ids, const float* renders, const float* TCO_in,
+                      const int32_t* label_ids, const void* renders, int render_u8, const float* TCO_in,
                       float* TCO_out, float* K_crop, float* boxes_rend, float* boxes_crop,
                       float* pose9, void* stream) {
   if (int rc = check_batch(h, B, "refine_n")) return rc;
@@ -508,10 +569,32 @@ int cosyb200_refine_n(cosyb200_handle* h, int slot, int B, int n_iter, const flo
                                    boxes_crop + (size_t)n * B * 4, K_crop + (size_t)n * B * 9, stream);
     if (rc) return rc;
     rc = cosyb200_refine_iter(h, slot, B, images, n_images, img_h, img_w, im_ids,
-                              boxes_crop + (size_t)n * B * 4, renders + (size_t)n * B * 3 * RENDER_H * RENDER_W,
-                              K_crop + (size_t)n * B * 9, tin, pose9 + (size_t)n * B * POSE_DIM,
+                              boxes_crop + (size_t)n * B * 4,
+                              (const char*)renders + (size_t)n * B * 3 * RENDER_H * RENDER_W * (render_u8 ? 1 : 4),
+                              render_u8, K_crop + (size_t)n * B * 9, tin, pose9 + (size_t)n * B * POSE_DIM,
                               TCO_out + (size_t)n * B * 16, stream);
     if (rc) return rc;
+  }
+  return COSYB200_OK;
+}
+
+// ---- launch accounting ------------------------------------------------------------------------
+int cosyb200_profile_enable(cosyb200_handle* h, int on) {
+  CB_CHECK_ARG(h != nullptr, "profile_enable: null handle");
+  DeviceGuard guard(h->device);
+  if (int rc = prof_resolve(h)) return rc;
+  h->profiling = on != 0;
+  return COSYB200_OK;
+}
+
+int cosyb200_profile_read(cosyb200_handle* h, int reset, int64_t* launches10, double* ms10) {
+  CB_CHECK_ARG(h != nullptr, "profile_read: null handle");
+  DeviceGuard guard(h->device);
+  if (int rc = prof_resolve(h)) return rc;
+  for (int i = 0; i < cosyb200_handle::N_CAT; ++i) {
+    if (launches10) launches10[i] = h->launches[i];
+    if (ms10) ms10[i] = h->cat_ms[i];
+    if (reset) { h->launches[i] = 0; h->cat_ms[i] = 0; }
   }
   return COSYB200_OK;
 }
@@ -545,6 +628,7 @@ int cosyb200_ransac_models(cosyb200_handle* h, int64_t n_seeds, const float* pos
   DeviceGuard guard(h->device);
   cudaStream_t st = (cudaStream_t)stream;
   int gs = pick_gs(h->s_max);
+  LaunchScope ls(h, CAT_RANSAC, st);
   DISPATCH_GS(gs, k_ransac_models, n_seeds, n_seeds, poses, cand_labels, seeds, h->aabb, h->sym, h->n_sym, h->s_max, TC1C2);
   CB_LAUNCH_CHECK();
   return COSYB200_OK;
@@ -558,6 +642,7 @@ int cosyb200_ransac_score(cosyb200_handle* h, int64_t n, const float* poses, con
   DeviceGuard guard(h->device);
   cudaStream_t st = (cudaStream_t)stream;
   int gs = pick_gs(h->s_max);
+  LaunchScope ls(h, CAT_RANSAC, st);
   DISPATCH_GS(gs, k_ransac_score, n, n, poses, cand_labels, tmatches, TC1C2, h->aabb, h->sym, h->s_max, dists);
   CB_LAUNCH_CHECK();
   return COSYB200_OK;
@@ -571,6 +656,7 @@ int cosyb200_symmetric_distance(cosyb200_handle* h, int64_t n, const float* T1, 
   DeviceGuard guard(h->device);
   cudaStream_t st = (cudaStream_t)stream;
   int gs = pick_gs(h->s_max);
+  LaunchScope ls(h, CAT_RANSAC, st);
   DISPATCH_GS(gs, k_symmetric_distance, n, n, T1, T2, label_ids, h->aabb, h->sym, h->s_max, dists, best_sym);
   CB_LAUNCH_CHECK();
   return COSYB200_OK;

@@ -99,4 +99,39 @@ struct cosyb200_handle {
   float* crops = nullptr;              // [B][3][240][320]
   float* pose9 = nullptr;              // [B][9] scratch
   size_t act_elems = 0, e_elems = 0, d_elems = 0, partial_elems = 0;
+  // launch accounting / optional per-category device timing (cosyb200_profile_*)
+  static constexpr int N_CAT = 10;
+  int64_t launches[N_CAT] = {0};
+  double cat_ms[N_CAT] = {0};
+  bool profiling = false;
+  std::vector<cudaEvent_t> ev_pool;   // pairs: [2*i] start, [2*i+1] stop
+  std::vector<int> ev_cat;            // category of each recorded pair
+  cudaStream_t ev_stream = nullptr;
 };
+
+namespace cosyb {
+enum Cat { CAT_GEOMETRY = 0, CAT_CROP, CAT_STEM, CAT_EXPAND, CAT_DW, CAT_SE, CAT_PROJECT, CAT_HEAD,
+           CAT_POOL_FC, CAT_RANSAC };
+int prof_resolve(cosyb200_handle* h);
+// Scope object: counts the launch and, when profiling, brackets it with events on `st`.
+struct LaunchScope {
+  cosyb200_handle* h;
+  cudaStream_t st;
+  bool rec = false;
+  LaunchScope(cosyb200_handle* h_, int cat, cudaStream_t st_) : h(h_), st(st_) {
+    h->launches[cat] += 1;
+    if (!h->profiling) return;
+    if (h->ev_cat.size() * 2 + 2 > h->ev_pool.size()) {
+      if (h->ev_pool.size() >= 16384) prof_resolve(h);
+      else for (int i = 0; i < 2; ++i) { cudaEvent_t e; cudaEventCreate(&e); h->ev_pool.push_back(e); }
+    }
+    h->ev_stream = st;
+    cudaEventRecord(h->ev_pool[h->ev_cat.size() * 2], st);
+    h->ev_cat.push_back(cat);
+    rec = true;
+  }
+  ~LaunchScope() {
+    if (rec) cudaEventRecord(h->ev_pool[(h->ev_cat.size() - 1) * 2 + 1], st);
+  }
+};
+}  // namespace cosyb

@@ -25,8 +25,11 @@ constexpr int STEM_CO = 40;
 constexpr int STEM_SMEM = STEM_TX * STEM_TY * STEM_CO;       // 10240 floats, aliased for the epilogue
 static_assert(IN_CH * STEM_IH * STEM_IWP + 54 * STEM_CO <= STEM_SMEM, "stem smem");
 
+// U8: the rendered view arrives as uint8 NHWC [B][240][320][3], the format the reference's renderer
+// hands over before `.float() / 255` (rendering/bullet_batch_renderer.py:70-83); converted here.
+template <bool U8>
 __global__ void __launch_bounds__(STEM_TX* STEM_TY)
-k_stem(const float* __restrict__ crops, const float* __restrict__ renders,
+k_stem(const float* __restrict__ crops, const void* __restrict__ renders_any,
        const float* __restrict__ w /*[54][40]*/, const float* __restrict__ bias, float* __restrict__ out) {
   constexpr int H = RENDER_H, W = RENDER_W, HO = H / 2, WO = W / 2;
   __shared__ __align__(16) float smem[STEM_SMEM];
@@ -42,8 +45,15 @@ k_stem(const float* __restrict__ crops, const float* __restrict__ renders,
     int gy = 2 * oy0 + iy, gx = 2 * ox0 + ix;   // pad (0,1): only the high side can fall outside
     float v = 0.f;
     if (gy < H && gx < W) {
-      const float* src = c < 3 ? crops : renders;
-      v = __ldg(src + (((size_t)b * 3 + (c % 3)) * H + gy) * W + gx);
+      if (c < 3) {
+        v = __ldg(crops + (((size_t)b * 3 + c) * H + gy) * W + gx);
+      } else if (U8) {
+        const uint8_t* r8 = static_cast<const uint8_t*>(renders_any);
+        v = __fdiv_rn((float)__ldg(r8 + (((size_t)b * H + gy) * W + gx) * 3 + (c - 3)), 255.0f);
+      } else {
+        const float* rf = static_cast<const float*>(renders_any);
+        v = __ldg(rf + (((size_t)b * 3 + (c - 3)) * H + gy) * W + gx);
+      }
     }
     s_in[(c * STEM_IH + iy) * STEM_IWP + ix] = v;
   }
@@ -283,6 +293,118 @@ k_dwconv(const float* __restrict__ in, const float* __restrict__ w /*[KS*KS][C]*
       s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
     }
     *reinterpret_cast<float4*>(partial + ((size_t)b * tiles_per_img + tile) * C + c) = s;
+  }
+}
+
+// Stride-1 depthwise with a rolling window: a thread owns (channel vector, output column) and walks
+// down TH output rows.  Each input row is loaded once per thread (KS vector loads, horizontally
+// shared through L1) and accumulated into the KS output rows it touches, held in a register ring;
+// the KS*KS taps of the thread's channels stay in registers.  Loads per output drop from KS^2 to ~KS.
+//   grid = (tiles_x * tiles_y, n_chunks, B); block = Gc * PX threads
+template <int V> struct VecT;
+template <> struct VecT<4> { using T = float4; };
+template <> struct VecT<2> { using T = float2; };
+__device__ __forceinline__ float4 pack_vec(const float (&a)[4]) { return make_float4(a[0], a[1], a[2], a[3]); }
+__device__ __forceinline__ float2 pack_vec(const float (&a)[2]) { return make_float2(a[0], a[1]); }
+template <int V> __device__ __forceinline__ void vzero(float* a) {
+#pragma unroll
+  for (int i = 0; i < V; ++i) a[i] = 0.f;
+}
+
+template <int KS, int V>
+__global__ void __launch_bounds__(DW_MAX_THREADS)
+k_dwconv_s1(const float* __restrict__ in, const float* __restrict__ w /*[KS*KS][C]*/,
+            const float* __restrict__ bias, float* __restrict__ out, float* __restrict__ partial,
+            int H, int W, int C, int pad, int Gc, int PX, int TH, int tiles_x, int tiles_per_img) {
+  using VT = typename VecT<V>::T;
+  __shared__ float sred[DW_MAX_THREADS * V];
+  const int b = blockIdx.z, tile = blockIdx.x;
+  const int tile_x = tile % tiles_x, tile_y = tile / tiles_x;
+  const int tid = threadIdx.x;
+  const int c = (blockIdx.y * Gc + tid % Gc) * V;
+  const int ox = tile_x * PX + tid / Gc;
+  const int oy0 = tile_y * TH;
+  const bool col_ok = ox < W;
+  const float* inb = in + (size_t)b * H * W * C + c;
+  float* outb = out + (size_t)b * H * W * C + c;
+
+  float wreg[KS * KS][V];
+#pragma unroll
+  for (int t = 0; t < KS * KS; ++t) {
+    VT wv = __ldg(reinterpret_cast<const VT*>(w + (size_t)t * C + c));
+    const float* wp = reinterpret_cast<const float*>(&wv);
+#pragma unroll
+    for (int i = 0; i < V; ++i) wreg[t][i] = wp[i];
+  }
+  float bv[V];
+  {
+    VT t = __ldg(reinterpret_cast<const VT*>(bias + c));
+    const float* tp = reinterpret_cast<const float*>(&t);
+#pragma unroll
+    for (int i = 0; i < V; ++i) bv[i] = tp[i];
+  }
+  float acc[KS][V];
+#pragma unroll
+  for (int s = 0; s < KS; ++s) vzero<V>(acc[s]);
+  float psum[V];
+  vzero<V>(psum);
+
+  const int n_in_rows = TH + KS - 1;
+  for (int r0 = 0; r0 < n_in_rows; r0 += KS) {
+#pragma unroll
+    for (int j = 0; j < KS; ++j) {
+      const int r = r0 + j;
+      const int iy = oy0 - pad + r;
+      if (r < n_in_rows && iy >= 0 && iy < H && col_ok) {
+        float v[KS][V];
+#pragma unroll
+        for (int kx = 0; kx < KS; ++kx) {
+          const int ix = ox - pad + kx;
+          if (ix >= 0 && ix < W) {
+            VT t = *reinterpret_cast<const VT*>(inb + ((size_t)iy * W + ix) * C);
+            const float* tp = reinterpret_cast<const float*>(&t);
+#pragma unroll
+            for (int i = 0; i < V; ++i) v[kx][i] = tp[i];
+          } else {
+            vzero<V>(v[kx]);
+          }
+        }
+        // input row r feeds output row (r - ky) with tap row ky; ring slot (j - ky) mod KS
+#pragma unroll
+        for (int ky = 0; ky < KS; ++ky) {
+          const int slot = (j - ky + KS) % KS;
+#pragma unroll
+          for (int kx = 0; kx < KS; ++kx)
+#pragma unroll
+            for (int i = 0; i < V; ++i) acc[slot][i] = fmaf(v[kx][i], wreg[ky * KS + kx][i], acc[slot][i]);
+        }
+      }
+      // output row (r - KS + 1) has now seen all of its input rows
+      const int slot_done = (j + 1) % KS;
+      const int oyr = r - (KS - 1);
+      if (oyr >= 0 && oyr < TH && oy0 + oyr < H && col_ok) {
+        float o[V];
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          o[i] = swishf(acc[slot_done][i] + bv[i]);
+          psum[i] += o[i];
+        }
+        *reinterpret_cast<VT*>(outb + ((size_t)(oy0 + oyr) * W + ox) * C) = pack_vec(o);
+      }
+      vzero<V>(acc[slot_done]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < V; ++i) sred[tid * V + i] = psum[i];
+  __syncthreads();
+  if (tid < Gc) {
+    float s[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) s[i] = sred[tid * V + i];
+    for (int q = 1; q < PX; ++q)
+#pragma unroll
+      for (int i = 0; i < V; ++i) s[i] += sred[(q * Gc + tid) * V + i];
+    *reinterpret_cast<VT*>(partial + ((size_t)b * tiles_per_img + tile) * C + c) = pack_vec(s);
   }
 }
 

@@ -64,6 +64,14 @@ class Engine:
             assert tuple(t.shape) == tuple(shape), f'{name} has shape {tuple(t.shape)}, expected {tuple(shape)}'
         return t
 
+    def _chk_renders(self, renders, lead):
+        """fp32 NCHW [..,3,240,320] -> 0, uint8 NHWC [..,240,320,3] -> 1 (render_u8 flag)."""
+        if renders.dtype == torch.uint8:
+            self._chk(renders, torch.uint8, tuple(lead) + (RENDER_H, RENDER_W, 3), 'renders (uint8 NHWC)')
+            return 1
+        self._chk(renders, torch.float32, tuple(lead) + (3, RENDER_H, RENDER_W), 'renders')
+        return 0
+
     def _new(self, *shape, dtype=torch.float32):
         return torch.empty(shape, dtype=dtype, device=self.device)
 
@@ -168,12 +176,12 @@ class Engine:
         self._chk(images, torch.float32, name='images')
         self._chk(im_ids, torch.int32, (B,), 'im_ids')
         self._chk(boxes_crop, torch.float32, (B, 4), 'boxes_crop')
-        self._chk(renders, torch.float32, (B, 3, RENDER_H, RENDER_W), 'renders')
+        u8 = self._chk_renders(renders, (B,))
         self._chk(K_crop, torch.float32, (B, 3, 3), 'K_crop')
         self._chk(TCO, torch.float32, (B, 4, 4), 'TCO')
         pose9, TCO_out = self._new(B, 9), self._new(B, 4, 4)
         _lib.check(self._L.cosyb200_refine_iter(
-            self._h, slot, B, _ptr(images), n_im, H, W, _ptr(im_ids), _ptr(boxes_crop), _ptr(renders),
+            self._h, slot, B, _ptr(images), n_im, H, W, _ptr(im_ids), _ptr(boxes_crop), _ptr(renders), u8,
             _ptr(K_crop), _ptr(TCO), _ptr(pose9), _ptr(TCO_out), self._stream()), 'refine_iter')
         return pose9, TCO_out
 
@@ -186,7 +194,7 @@ class Engine:
         self._chk(im_ids, torch.int32, (B,), 'im_ids')
         self._chk(K, torch.float32, (B, 3, 3), 'K')
         self._chk(label_ids, torch.int32, (B,), 'label_ids')
-        self._chk(renders, torch.float32, (n_iter, B, 3, RENDER_H, RENDER_W), 'renders')
+        u8 = self._chk_renders(renders, (n_iter, B))
         self._chk(TCO, torch.float32, (B, 4, 4), 'TCO')
         if out is None:
             out = dict(TCO_output=self._new(n_iter, B, 4, 4), K_crop=self._new(n_iter, B, 3, 3),
@@ -194,9 +202,23 @@ class Engine:
                        pose=self._new(n_iter, B, 9))
         _lib.check(self._L.cosyb200_refine_n(
             self._h, slot, B, n_iter, _ptr(images), n_im, H, W, _ptr(im_ids), _ptr(K), _ptr(label_ids),
-            _ptr(renders), _ptr(TCO), _ptr(out['TCO_output']), _ptr(out['K_crop']), _ptr(out['boxes_rend']),
+            _ptr(renders), u8, _ptr(TCO), _ptr(out['TCO_output']), _ptr(out['K_crop']), _ptr(out['boxes_rend']),
             _ptr(out['boxes_crop']), _ptr(out['pose']), self._stream()), 'refine_n')
         return out
+
+    # -- launch accounting --------------------------------------------------------------------
+    CATEGORIES = ('geometry', 'roi_crop', 'stem', 'expand_1x1', 'depthwise', 'squeeze_excite',
+                  'project_1x1', 'head_1x1', 'pool_fc_update', 'ransac')
+
+    def profile_enable(self, on=True):
+        _lib.check(self._L.cosyb200_profile_enable(self._h, int(on)), 'profile_enable')
+
+    def profile_read(self, reset=True):
+        """{category: (launches, device_ms)} since the last reset (ms only while profiling)."""
+        n = np.zeros(10, dtype=np.int64)
+        ms = np.zeros(10, dtype=np.float64)
+        _lib.check(self._L.cosyb200_profile_read(self._h, int(reset), _np_ptr(n), _np_ptr(ms)), 'profile_read')
+        return {c: (int(n[i]), float(ms[i])) for i, c in enumerate(self.CATEGORIES)}
 
     # -- multiview ----------------------------------------------------------------------------
     def ransac_models(self, poses, cand_label_ids, seeds):

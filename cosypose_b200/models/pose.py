@@ -100,7 +100,9 @@ class PosePredictor:
             boxes_rend, boxes_crop, K_crop = eng.prepare_iter(K, TCO_input, label_ids, img_hw)
             renders = self.renderer.render(obj_infos=obj_infos, TCO=TCO_input, K=K_crop,
                                            resolution=self.render_size)
-            renders = renders.to(eng.device, torch.float32).contiguous()
+            renders = renders.to(eng.device).contiguous()
+            if renders.dtype != torch.uint8:
+                renders = renders.float()
             pose9, TCO_output = eng.refine_iter(self.slot, images, im_ids, boxes_crop, renders, K_crop, TCO_input)
             outputs[f'iteration={n + 1}'] = {
                 'TCO_input': TCO_input,

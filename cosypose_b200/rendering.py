@@ -22,6 +22,19 @@ class PreRenderedViews:
                 self.chunks.append(c.to(device) if device is not None else c)
         self.reset()
 
+    @classmethod
+    def from_uint8(cls, stages, bsz_objects=64):
+        """stages: device tensors [n_iter_s, N, 240, 320, 3] uint8 (NHWC, as the reference's renderer
+        delivers them); consumed by the engine without a conversion pass."""
+        self = cls.__new__(cls)
+        self.bsz = bsz_objects
+        self.chunks = []
+        for views in stages:
+            for s in range(0, views.shape[1], bsz_objects):
+                self.chunks.append(views[:, s:s + bsz_objects].contiguous())
+        self.reset()
+        return self
+
     def reset(self):
         self._chunk = 0
         self._it = 0

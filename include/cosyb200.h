@@ -108,11 +108,14 @@ int cosyb200_update_pose(cosyb200_handle* h, int B, const float* TCO_in_dev,
                          void* stream);
 
 /* Phase B of one iteration: crop + concat + backbone + head + pose update
- * (reference: models/pose.py:99-108 minus the renderer call).  Images are gathered through
+ * (reference: models/pose.py:99-108 minus the renderer call).  renders_dev is fp32 NCHW
+ * [B,3,240,320] in [0,1] (render_u8 == 0, the tensor pose.py:100 receives) or uint8 NHWC
+ * [B,240,320,3] (render_u8 == 1, what the renderer produces before `.float()/255`,
+ * rendering/bullet_batch_renderer.py:70-83; converted inside the stem kernel).  Images are gathered through
  * im_ids_dev instead of being copied per hypothesis (pose_predictor.py:41). */
 int cosyb200_refine_iter(cosyb200_handle* h, int slot, int B, const float* images_dev,
                          int n_images, int img_h, int img_w, const int32_t* im_ids_dev,
-                         const float* boxes_crop_dev, const float* renders_dev,
+                         const float* boxes_crop_dev, const void* renders_dev, int render_u8,
                          const float* K_crop_dev, const float* TCO_in_dev, float* pose9_dev,
                          float* TCO_out_dev, void* stream);
 
@@ -122,9 +125,18 @@ int cosyb200_refine_iter(cosyb200_handle* h, int slot, int B, const float* image
  * boxes_crop [n_iter,B,4], pose9 [n_iter,B,9]; iteration n reads TCO_out[n-1] (TCO_in_dev for n=0). */
 int cosyb200_refine_n(cosyb200_handle* h, int slot, int B, int n_iter, const float* images_dev,
                       int n_images, int img_h, int img_w, const int32_t* im_ids_dev,
-                      const float* K_dev, const int32_t* label_ids_dev, const float* renders_dev,
-                      const float* TCO_in_dev, float* TCO_out_dev, float* K_crop_dev,
+                      const float* K_dev, const int32_t* label_ids_dev, const void* renders_dev,
+                      int render_u8, const float* TCO_in_dev, float* TCO_out_dev, float* K_crop_dev,
                       float* boxes_rend_dev, float* boxes_crop_dev, float* pose9_dev, void* stream);
+
+/* Launch accounting (no reference counterpart; the reference times with a wall-clock Timer,
+ * utils/timer.py:4-36).  Every kernel the engine launches is counted per category:
+ *   0 geometry, 1 roi crop, 2 stem, 3 expand 1x1, 4 depthwise, 5 squeeze-excite, 6 project 1x1,
+ *   7 head 1x1, 8 pool+fc+update, 9 ransac.
+ * With profiling enabled each launch is also bracketed by CUDA events on its stream and the
+ * device time accumulated per category (adds launch overhead: use outside timed regions). */
+int cosyb200_profile_enable(cosyb200_handle* h, int on);
+int cosyb200_profile_read(cosyb200_handle* h, int reset, int64_t* launches10, double* ms10);
 
 /* ---- multiview candidate matching (reference: multiview/ransac.py:137-199) ---- */
 

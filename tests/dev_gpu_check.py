@@ -7,7 +7,8 @@ import torch
 from cosypose_b200 import synthetic as syn, effnet_spec as spec
 from cosypose_b200.engine import Engine
 from oracle import pose_oracle as po
-from tests.helpers import Workload, build_predictor, state_dict
+sys.path.insert(0, str(Path(__file__).resolve().parent))
+from helpers import Workload, build_predictor, state_dict
 
 torch.manual_seed(0)
 dev = torch.device('cuda', 0)
