@@ -42,6 +42,9 @@ _SIGS = {
     'cosyb200_ransac_models': ([_P, c_int64, _P, _P, _P, _P, _P], c_int),
     'cosyb200_ransac_score': ([_P, c_int64, _P, _P, _P, _P, _P, _P], c_int),
     'cosyb200_symmetric_distance': ([_P, c_int64, _P, _P, _P, _P, _P, _P], c_int),
+    'cosyb200_compose_inv': ([_P, c_int64, _P, _P, _P, _P, _P, _P], c_int),
+    'cosyb200_ba_linearize': ([_P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, c_float,
+                               _P, _P, _P, _P, _P, _P, _P, _P], c_int),
     'cosyb200_ransac_inliers': ([c_int64, _P, _P, c_int64, _P, _P, _P, _P, c_float, c_int, _P, _P,
                                  POINTER(c_int64), _P, POINTER(c_int64)], c_int),
     'cosyb200_scatter_argmin': ([c_int64, _P, _P, c_int64, _P], c_int),

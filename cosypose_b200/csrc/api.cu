@@ -10,6 +10,7 @@
 #include "kernels_crop.cuh"
 #include "kernels_geometry.cuh"
 #include "kernels_ransac.cuh"
+#include "kernels_ba.cuh"
 
 namespace cosyb {
 
@@ -659,6 +660,58 @@ int cosyb200_symmetric_distance(cosyb200_handle* h, int64_t n, const float* T1, 
   LaunchScope ls(h, CAT_RANSAC, st);
   DISPATCH_GS(gs, k_symmetric_distance, n, n, T1, T2, label_ids, h->aabb, h->sym, h->s_max, dists, best_sym);
   CB_LAUNCH_CHECK();
+  return COSYB200_OK;
+}
+
+int cosyb200_compose_inv(cosyb200_handle* h, int64_t n, const float* A, const int32_t* ia, const float* B,
+                         const int32_t* ib, float* out, void* stream) {
+  CB_CHECK_ARG(h != nullptr && n >= 0 && A && B && out, "compose_inv: bad arguments");
+  if (n == 0) return COSYB200_OK;
+  DeviceGuard guard(h->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  LaunchScope ls(h, CAT_RANSAC, st);
+  k_compose_inv<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(n, A, ia, B, ib, out);
+  CB_LAUNCH_CHECK();
+  return COSYB200_OK;
+}
+
+int cosyb200_ba_linearize(cosyb200_handle* h, int n_cand, int n_obj, int n_view, int n_pts,
+                          const float* cand_TCO, const int32_t* cand_obj, const int32_t* cand_view,
+                          const int32_t* cand_label, const float* TWO_9d, const float* TCW_9d,
+                          const float* K, const float* points, float residuals_threshold,
+                          float* align_dists, float* aligned, float* errors, float* Jc, float* JtJ,
+                          float* Jte, float* loss, void* stream) {
+  CB_CHECK_ARG(h != nullptr && n_cand >= 1 && n_obj >= 1 && n_view >= 1 && n_pts >= 1, "ba_linearize: bad sizes");
+  CB_CHECK_ARG(cand_TCO && cand_obj && cand_view && cand_label && TWO_9d && TCW_9d && K && points,
+               "ba_linearize: null input");
+  CB_CHECK_ARG(align_dists && aligned && errors && Jc && loss, "ba_linearize: null output");
+  if (!h->sym) { set_error("ba_linearize: meshes not set"); return COSYB200_ESTATE; }
+  DeviceGuard guard(h->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  {
+    LaunchScope ls(h, CAT_RANSAC, st);
+    k_ba_align<<<(n_cand + 63) / 64, 64, 0, st>>>(n_cand, n_pts, cand_TCO, cand_obj, cand_view, cand_label, TWO_9d,
+                                                  TCW_9d, K, points, h->sym, h->n_sym, h->s_max, align_dists, aligned);
+  }
+  CB_LAUNCH_CHECK();
+  {
+    LaunchScope ls(h, CAT_RANSAC, st);
+    k_ba_residuals<<<(n_cand * n_pts + 63) / 64, 64, 0, st>>>(n_cand, n_pts, aligned, cand_obj, cand_view, cand_label,
+                                                              TWO_9d, TCW_9d, K, points, errors, Jc);
+  }
+  CB_LAUNCH_CHECK();
+  {
+    LaunchScope ls(h, CAT_RANSAC, st);
+    k_ba_loss<<<1, 256, 0, st>>>(n_cand * n_pts * 2, errors, residuals_threshold, loss);
+  }
+  CB_LAUNCH_CHECK();
+  if (JtJ && Jte) {
+    const int n_params = 9 * (n_obj + n_view);
+    dim3 block(32, 8), grid((n_params + 1 + 31) / 32, (n_params + 7) / 8);
+    LaunchScope ls(h, CAT_RANSAC, st);
+    k_ba_normal<<<grid, block, 0, st>>>(n_cand, n_pts, n_obj, n_view, cand_obj, cand_view, Jc, errors, JtJ, Jte);
+    CB_LAUNCH_CHECK();
+  }
   return COSYB200_OK;
 }
 

@@ -253,6 +253,42 @@ class Engine:
         return dists, best
 
 
+    def compose_inv(self, A, B, ia=None, ib=None):
+        """inv(A[ia]) @ B[ib] for rigid transforms."""
+        self._chk(A, torch.float32, name='A')
+        self._chk(B, torch.float32, name='B')
+        n = len(ia) if ia is not None else (len(ib) if ib is not None else A.shape[0])
+        for idx in (ia, ib):
+            if idx is not None:
+                self._chk(idx, torch.int32, (n,), 'index')
+        out = self._new(n, 4, 4)
+        _lib.check(self._L.cosyb200_compose_inv(self._h, n, _ptr(A), _ptr(ia), _ptr(B), _ptr(ib), _ptr(out),
+                                                self._stream()), 'compose_inv')
+        return out
+
+    def ba_linearize(self, cand_TCO, cand_obj, cand_view, cand_label, TWO_9d, TCW_9d, K, points,
+                     residuals_threshold=25.0, normal_equations=True):
+        n_cand, n_obj, n_view, n_pts = cand_TCO.shape[0], TWO_9d.shape[0], TCW_9d.shape[0], points.shape[1]
+        self._chk(cand_TCO, torch.float32, (n_cand, 4, 4), 'cand_TCO')
+        for t, nm in ((cand_obj, 'cand_obj'), (cand_view, 'cand_view'), (cand_label, 'cand_label')):
+            self._chk(t, torch.int32, (n_cand,), nm)
+        self._chk(TWO_9d, torch.float32, (n_obj, 9), 'TWO_9d')
+        self._chk(TCW_9d, torch.float32, (n_view, 9), 'TCW_9d')
+        self._chk(K, torch.float32, (n_view, 3, 3), 'K')
+        self._chk(points, torch.float32, (points.shape[0], n_pts, 3), 'points')
+        n_res, n_params = n_cand * n_pts * 2, 9 * (n_obj + n_view)
+        out = dict(align_dists=self._new(n_cand), aligned=self._new(n_cand, 4, 4), errors=self._new(n_res),
+                   Jc=self._new(n_res, 18), loss=self._new(1),
+                   JtJ=self._new(n_params, n_params) if normal_equations else None,
+                   Jte=self._new(n_params) if normal_equations else None)
+        _lib.check(self._L.cosyb200_ba_linearize(
+            self._h, n_cand, n_obj, n_view, n_pts, _ptr(cand_TCO), _ptr(cand_obj), _ptr(cand_view),
+            _ptr(cand_label), _ptr(TWO_9d), _ptr(TCW_9d), _ptr(K), _ptr(points), float(residuals_threshold),
+            _ptr(out['align_dists']), _ptr(out['aligned']), _ptr(out['errors']), _ptr(out['Jc']),
+            _ptr(out['JtJ']), _ptr(out['Jte']), _ptr(out['loss']), self._stream()), 'ba_linearize')
+        return out
+
+
 # -- host-side tables ----------------------------------------------------------------------------
 
 def sample_point_ids(n_points_max, n_points=2000):

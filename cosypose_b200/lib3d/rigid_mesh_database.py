@@ -96,10 +96,31 @@ class BatchedMeshes(TensorCollection):
     def aabb(self):
         return torch.as_tensor(aabb_corners(self.points.cpu().numpy()))
 
+    def batched(self, aabb=False, resample_n_points=None, n_sym=None):
+        """Same role as the reference's MeshDataBase.batched (rigid_mesh_database.py:21-56) on tables
+        that are already stacked: `aabb=True` replaces each cloud by its 8 box corners
+        (lib3d/mesh_ops.py:15-28); `resample_n_points` keeps a seeded subset of the vertices (the
+        reference samples the mesh surface with trimesh, which needs the faces and is outside the
+        path).  Symmetry sets are shared."""
+        if aabb:
+            assert resample_n_points is None
+            points = self.aabb().to(self.points.device, self.points.dtype)
+        elif resample_n_points:
+            ids = np.random.RandomState(0).choice(self.points.shape[1], size=resample_n_points,
+                                                  replace=self.points.shape[1] < resample_n_points)
+            points = self.points[:, torch.as_tensor(ids)]
+        else:
+            points = self.points
+        out = BatchedMeshes(self.infos, list(self.labels), points.clone(), self.symmetries)
+        out.engine = getattr(self, 'engine', None)
+        return out
+
     def install(self, engine, with_points=True):
-        """Uploads the tables into an engine handle (cosyb200_set_meshes)."""
+        """Uploads the tables into an engine handle (cosyb200_set_meshes) and remembers the
+        engine (`self.engine`) for the multiview stages."""
         pts = self.points.cpu().numpy()
         ids = sample_point_ids(pts.shape[1]) if with_points and pts.shape[1] >= 2000 else None
         engine.set_meshes(pts if ids is not None else None, self.symmetries, self.n_sym_array(),
                           aabb=aabb_corners(pts), point_ids=ids)
+        self.engine = engine
         return engine

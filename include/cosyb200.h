@@ -190,6 +190,30 @@ int cosyb200_expand_ids_for_symmetry(int64_t n, const int32_t* label_ids_host,
                                      const int32_t* n_sym_per_label_host, int64_t* n_out,
                                      int32_t* ids_expand_host, int32_t* sym_ids_host);
 
+/* out[i] = inv(A[ia[i]]) @ B[ib[i]] for rigid 4x4 transforms (ia / ib may be NULL = identity map):
+ * `invert_T(TWC) @ TWO` of reproject_scene (reference: integrated/multiview_predictor.py:20-41) and
+ * the known-camera branch `invert_T(TWC1) @ TWC2` (multiview/ransac.py:169-173). */
+int cosyb200_compose_inv(cosyb200_handle* h, int64_t n, const float* A_dev, const int32_t* ia_dev,
+                         const float* B_dev, const int32_t* ib_dev, float* out_dev, void* stream);
+
+/* One linearisation of the object-level bundle adjustment problem = MultiviewRefinement.
+ * align_TCO_cand + forward_jacobian (reference: multiview/bundle_adjustment.py:164-214) with analytic
+ * derivatives instead of autograd, plus the normal equations of compute_lm_step (:216-222).
+ *   cand_TCO [n_cand,4,4], cand_obj / cand_view / cand_label [n_cand] (local object / view ids,
+ *   dense label ids), TWO_9d [n_obj,9], TCW_9d [n_view,9], K [n_view,3,3], points [n_labels,n_pts,3]
+ *   -> align_dists [n_cand], aligned [n_cand,4,4] (candidate poses times their best symmetry),
+ *      errors [n_res] (n_res = n_cand*n_pts*2, order candidate, point, x|y), Jc [n_res,18]
+ *      (d yhat / d TWO_9d[obj] | d yhat / d TCW_9d[view]), loss [1] = mean(min(e^2, threshold)),
+ *      and when non-NULL JtJ [n_params,n_params], Jte [n_params] with n_params = 9*(n_obj+n_view),
+ *      object parameters first.  The small dense solve stays with the caller, as in the reference. */
+int cosyb200_ba_linearize(cosyb200_handle* h, int n_cand, int n_obj, int n_view, int n_pts,
+                          const float* cand_TCO_dev, const int32_t* cand_obj_dev,
+                          const int32_t* cand_view_dev, const int32_t* cand_label_dev,
+                          const float* TWO_9d_dev, const float* TCW_9d_dev, const float* K_dev,
+                          const float* points_dev, float residuals_threshold, float* align_dists_dev,
+                          float* aligned_dev, float* errors_dev, float* Jc_dev, float* JtJ_dev,
+                          float* Jte_dev, float* loss_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

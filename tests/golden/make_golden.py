@@ -159,6 +159,40 @@ def golden_multiview(cosypose, name, n_views, n_objects, n_labels, sym_counts, u
     print(name, 'matched', len(fc), 'pairs', len(out['pairs_view1']))
 
 
+def golden_scene_state(cosypose, name, n_views, n_objects, n_labels, sym_counts, n_ransac, ba_n_iter, seed=0):
+    """MultiviewScenePredictor.predict_scene_state of the reference (matching + BA + reprojection)."""
+    import cosypose.utils.tensor_collection as tc
+    from cosypose.integrated.multiview_predictor import MultiviewScenePredictor
+    from cosypose.lib3d.mesh_ops import get_meshes_bounding_boxes
+    labels = syn.make_labels(n_labels)
+    points, sym, n_sym = syn.make_mesh_tables(n_labels, n_points=64, sym_counts=sym_counts)
+    mesh_db = ref_mesh_db(cosypose, labels, get_meshes_bounding_boxes(points), sym, n_sym)
+    scene = syn.make_multiview_scene(n_views, n_objects, n_labels, seed=seed, unique_labels=True)
+    infos = pd.DataFrame(dict(view_id=scene['view_ids'], label=[labels[i] for i in scene['label_ids']],
+                              score=scene['scores'], scene_id=0, group_id=0, batch_im_id=scene['view_ids']))
+    cands = tc.PandasTensorCollection(infos=infos, poses=scene['poses'])
+    cam_infos = pd.DataFrame(dict(view_id=np.arange(n_views), scene_id=0, batch_im_id=np.arange(n_views)))
+    cameras = tc.PandasTensorCollection(infos=cam_infos, K=scene['K'], TWC=scene['TWC'])
+    pred = MultiviewScenePredictor.__new__(MultiviewScenePredictor)
+    pred.mesh_db_ransac = mesh_db
+    pred.mesh_db_ba = mesh_db
+    out = pred.predict_scene_state(cands, cameras, ransac_n_iter=n_ransac, ba_n_iter=ba_n_iter)
+    res = dict(meta=np.array([n_views, n_objects, n_labels, n_ransac, ba_n_iter, seed]),
+               sym_counts=np.array(sym_counts), chk_poses=checksum(scene['poses']),
+               objects_TWO=out['scene/objects'].TWO.numpy(),
+               objects_obj_id=out['scene/objects'].infos['obj_id'].values.astype(np.int64),
+               objects_n_cand=out['scene/objects'].infos['n_cand'].values.astype(np.int64),
+               cameras_TWC=out['scene/cameras'].TWC.numpy(),
+               cameras_view_id=out['scene/cameras'].infos['view_id'].values.astype(np.int64),
+               ba_output_poses=out['ba_output'].poses.numpy(),
+               ba_output_view_id=out['ba_output'].infos['view_id'].values.astype(np.int64),
+               ba_output_obj_id=out['ba_output'].infos['obj_id'].values.astype(np.int64),
+               ba_input_poses=out['ba_input'].poses.numpy(),
+               n_all=np.array([len(out['ba_output+all_cand'])]))
+    np.savez_compressed(HERE / f'{name}.npz', **res)
+    print(name, 'objects', len(res['objects_obj_id']), 'cameras', len(res['cameras_view_id']))
+
+
 def main():
     torch.manual_seed(0)
     cosypose = ref_harness.import_reference()
@@ -172,6 +206,8 @@ def main():
     golden_multiview(cosypose, 'multiview_small', 4, 6, 8, (1,), True, 50)
     golden_multiview(cosypose, 'multiview_sym', 3, 5, 4, (1, 2, 4, 8), False, 30, seed=3)
     golden_multiview(cosypose, 'multiview_cfg4', 8, 16, 21, (1,), True, 2000)
+    golden_scene_state(cosypose, 'scene_state_small', 4, 6, 8, (1,), 50, 3)
+    golden_scene_state(cosypose, 'scene_state_sym', 4, 5, 6, (1, 2, 4), 50, 10, seed=2)
 
 
 if __name__ == '__main__':

@@ -58,4 +58,10 @@ def import_reference():
     n_threads = torch.get_num_threads()
     import cosypose  # sets OMP/MKL env vars (cosypose/__init__.py:2-3); harmless after torch import
     torch.set_num_threads(n_threads)
+    if not torch.cuda.is_available():
+        # TensorCollection.cuda() is `.to('cuda')` (utils/tensor_collection.py:83-84), used by
+        # integrated/multiview_predictor.py:80; identity on a CPU-only box (runtime patch, the
+        # reference sources are untouched)
+        from cosypose.utils import tensor_collection as ref_tc
+        ref_tc.TensorCollection.cuda = lambda self: self
     return cosypose

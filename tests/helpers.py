@@ -54,3 +54,35 @@ def build_predictor(w, device, bsz_objects=64, per_call_renderer=False, max_batc
     coarse = PosePredictor(eng, 0, renderer, mesh_db).load_state_dict(state_dict(0))
     refiner = PosePredictor(eng, 1, renderer, mesh_db).load_state_dict(state_dict(1))
     return CoarseRefinePosePredictor(coarse, refiner, bsz_objects=bsz_objects), eng, views
+
+
+class Scene:
+    """Synthetic multiview scene (SURVEY.md section 8d, config 4 recipe) rebuilt from the meta of a
+    golden file: candidates, cameras, AABB mesh tables."""
+
+    def __init__(self, n_views, n_objects, n_labels, sym_counts=(1,), unique_labels=True, seed=0):
+        from cosypose_b200.engine import aabb_corners
+        self.labels = syn.make_labels(n_labels)
+        pts, self.sym, self.n_sym = syn.make_mesh_tables(n_labels, n_points=64, sym_counts=tuple(int(s) for s in sym_counts))
+        self.aabb = torch.as_tensor(aabb_corners(pts.numpy()))
+        s = syn.make_multiview_scene(n_views, n_objects, n_labels, seed=seed, unique_labels=unique_labels)
+        self.view_ids, self.label_ids, self.scores = s['view_ids'], s['label_ids'], s['scores']
+        self.poses, self.K, self.TWC, self.TWO = s['poses'], s['K'], s['TWC'], s['TWO']
+        self.n_views = n_views
+
+    def candidates(self, device=None):
+        from cosypose_b200.utils import tensor_collection as tc
+        infos = pd.DataFrame(dict(view_id=self.view_ids, label=[self.labels[i] for i in self.label_ids],
+                                  score=self.scores, scene_id=0, group_id=0, batch_im_id=self.view_ids))
+        poses = self.poses if device is None else self.poses.to(device)
+        return tc.PandasTensorCollection(infos=infos, poses=poses)
+
+    def cameras(self, device=None):
+        from cosypose_b200.utils import tensor_collection as tc
+        infos = pd.DataFrame(dict(view_id=np.arange(self.n_views), scene_id=0, batch_im_id=np.arange(self.n_views)))
+        K, TWC = (self.K, self.TWC) if device is None else (self.K.to(device), self.TWC.to(device))
+        return tc.PandasTensorCollection(infos=infos, K=K, TWC=TWC)
+
+    def mesh_db(self):
+        from cosypose_b200.lib3d.rigid_mesh_database import BatchedMeshes
+        return BatchedMeshes.from_tables(self.labels, self.aabb, self.sym, self.n_sym)

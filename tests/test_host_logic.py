@@ -1,0 +1,151 @@
+"""CPU tests of the host-side mirror of the reference interface: tensor collections, mesh tables,
+pre-rendered view sequencing, sharding and the world_size-2 gather (gloo), product import rules."""
+import os
+import pickle
+import subprocess
+import sys
+import textwrap
+from pathlib import Path
+
+import numpy as np
+import pandas as pd
+import pytest
+import torch
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def test_tensor_collection_semantics():
+    from cosypose_b200.utils import tensor_collection as tc
+    infos = pd.DataFrame(dict(label=['a', 'b', 'c'], view_id=[0, 0, 1]), index=[5, 6, 7])
+    c = tc.PandasTensorCollection(infos, poses=torch.arange(48.).view(3, 4, 4), score=torch.tensor([1., 2, 3]))
+    assert len(c) == 3 and list(c.infos.index) == [0, 1, 2]
+    sub = c[[2, 0]]
+    assert list(sub.infos['label']) == ['c', 'a'] and sub.poses.shape == (2, 4, 4) and sub.score.tolist() == [3., 1.]
+    assert c[np.array([1])].poses[0, 0, 0] == 16
+    c.poses = c.poses + 1                       # assignment to a registered name updates the tensor
+    assert c.tensors['poses'][0, 0, 0] == 1
+    c.extra = 'x'                               # other attributes are plain attributes
+    assert 'extra' not in c.tensors
+    with pytest.raises(AttributeError):
+        c.missing
+    m = c.merge_df(pd.DataFrame(dict(view_id=[0, 1], view_group=[7, 8])), on='view_id')
+    assert list(m.infos['view_group']) == [7, 7, 8]
+    cat = tc.concatenate([c, tc.PandasTensorCollection(pd.DataFrame()), sub])
+    assert len(cat) == 5 and cat.poses.shape == (5, 4, 4)
+    assert len(tc.concatenate([])) == 0
+    c2 = pickle.loads(pickle.dumps(c))
+    assert torch.equal(c2.poses, c.poses) and list(c2.infos['label']) == ['a', 'b', 'c']
+    cl = c.clone()
+    cl.poses[0, 0, 0] = -5
+    assert c.poses[0, 0, 0] == 1
+    assert c.float().poses.dtype == torch.float32 and c.device.type == 'cpu'
+    assert 'poses' in repr(c)
+
+
+def test_mesh_tables_padding_and_sampling():
+    from cosypose_b200.engine import aabb_corners, sample_point_ids
+    from cosypose_b200.lib3d.rigid_mesh_database import BatchedMeshes, pad_stack
+    rs = np.random.RandomState(0)
+    verts = [rs.rand(2100, 3), rs.rand(2500, 3), rs.rand(2001, 3)]
+    syms = [np.eye(4)[None], np.tile(np.eye(4), (3, 1, 1))]
+    db = BatchedMeshes.from_vertex_lists(['o1', 'o2', 'o3'], verts, syms + [np.eye(4)[None]])
+    assert db.points.shape == (3, 2500, 3) and db.symmetries.shape == (3, 3, 4, 4)
+    assert db.n_sym_mapping == {'o1': 1, 'o2': 3, 'o3': 1}
+    # padding re-draws own points (reference rule), identity pads symmetries
+    assert np.isin(db.points[0, 2100:].numpy().round(6), np.float32(verts[0]).round(6)).all()
+    assert torch.equal(db.symmetries[0, 1], torch.eye(4))
+    sel = db.select(np.array(['o3', 'o1', 'o3']))
+    assert sel.points.shape == (3, 2500, 3)
+    pts = sel.sample_points(2000, deterministic=True)
+    ids = sample_point_ids(2500)
+    assert torch.equal(pts, sel.points[:, torch.as_tensor(ids)])
+    assert len(np.unique(ids)) == 2000
+    with pytest.raises(KeyError):
+        db.select(['nope'])
+    box = aabb_corners(np.array([[[0., 0, 0], [1, 2, 3]]]))[0]
+    assert box.tolist()[0] == [0, 2, 3] and box.tolist()[6] == [1, 0, 0] and box.tolist()[7] == [0, 0, 0]
+    assert db.batched(aabb=True).points.shape == (3, 8, 3)
+    assert pad_stack([np.zeros((1, 2)), np.ones((3, 2))], fill=np.array([7., 7.]))[0, 2, 0] == 7
+
+
+def test_prerendered_view_sequencing():
+    from cosypose_b200.rendering import PerCallRenderer, PreRenderedViews
+    c = torch.arange(1 * 5, dtype=torch.float32).view(1, 5, 1, 1, 1).expand(1, 5, 3, 240, 320)
+    r = (100 + torch.arange(2 * 5, dtype=torch.float32)).view(2, 5, 1, 1, 1).expand(2, 5, 3, 240, 320)
+    v = PreRenderedViews([c, r], bsz_objects=4)
+    # coarse: chunks of 4 then 1, one iteration each; refiner: 2 iterations per chunk
+    assert v.prerendered(1, 4)[0, :, 0, 0, 0].tolist() == [0, 1, 2, 3]
+    assert v.prerendered(1, 1)[0, :, 0, 0, 0].tolist() == [4]
+    assert v.prerendered(2, 4)[1, :, 0, 0, 0].tolist() == [105, 106, 107, 108]
+    assert v.render([0], None, None)[:, 0, 0, 0].tolist() == [104]
+    assert v.render([0], None, None)[:, 0, 0, 0].tolist() == [109]
+    assert v.render([0] * 4, None, None)[:, 0, 0, 0].tolist() == [0, 1, 2, 3]      # wrapped around
+    assert not hasattr(PerCallRenderer(v), 'prerendered')
+    with pytest.raises(AssertionError):
+        v.prerendered(3, 4)
+
+
+def test_shard_bounds():
+    from cosypose_b200.sharding import shard_bounds
+    for n, ws in ((512, 8), (10, 4), (3, 8), (0, 2)):
+        spans = [shard_bounds(n, r, ws) for r in range(ws)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+    assert shard_bounds(512, 3, 8) == (192, 256)
+
+
+_GLOO_WORKER = textwrap.dedent('''
+    import sys, numpy as np, pandas as pd, torch, torch.distributed as dist
+    sys.path.insert(0, sys.argv[1])
+    from cosypose_b200.sharding import gather_poses, shard_bounds, world
+    from cosypose_b200.utils import tensor_collection as tc
+    dist.init_process_group('gloo')
+    rank, ws = world()
+    n = 7
+    full = torch.arange(n * 16, dtype=torch.float32).view(n, 4, 4)
+    a, b = shard_bounds(n, rank, ws)
+    out = gather_poses(full[a:b].clone(), n_total=n)
+    assert torch.equal(out, full), (rank, out)
+    # equal shards without n_total
+    out2 = gather_poses(torch.full((3, 4, 4), float(rank)))
+    assert out2.shape == (3 * ws, 4, 4) and out2[3 * rank, 0, 0] == rank
+    c = tc.PandasTensorCollection(pd.DataFrame(dict(i=np.arange(a, b))), poses=full[a:b].clone())
+    g = c.gather_distributed()
+    assert list(g.infos['i']) == list(range(n)) and torch.equal(g.poses, full)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.stdout.write('rank%dok ' % rank)
+    sys.stdout.flush()
+''')
+
+
+def test_gather_world_size_2_gloo(tmp_path):
+    """The N>1 exchange step on CPU: contiguous shards, one all-gather, every rank gets all poses."""
+    script = tmp_path / 'worker.py'
+    script.write_text(_GLOO_WORKER)
+    env = dict(os.environ, MASTER_ADDR='127.0.0.1', OMP_NUM_THREADS='1')
+    r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node=2',
+                        '--master-addr', '127.0.0.1', '--master-port', '29731', str(script), str(ROOT)],
+                       capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert 'rank0ok' in r.stdout and 'rank1ok' in r.stdout
+
+
+def test_product_never_imports_the_oracle():
+    """The product package must not import, call or link anything under oracle/ (checker only)."""
+    for p in (ROOT / 'cosypose_b200').rglob('*.py'):
+        text = p.read_text()
+        assert 'import oracle' not in text and 'from oracle' not in text, p
+    for p in (ROOT / 'cosypose_b200' / 'csrc').iterdir():
+        if p.suffix in ('.cu', '.cuh', '.h', '.cpp'):
+            assert 'oracle' not in p.read_text(), p
+
+
+def test_engine_fails_loudly_without_gpu():
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    from cosypose_b200 import _lib
+    from cosypose_b200.engine import Engine
+    with pytest.raises(_lib.EngineError):
+        Engine(0)
