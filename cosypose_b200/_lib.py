@@ -36,6 +36,9 @@ _SIGS = {
     'cosyb200_refine_iter': ([_P, c_int, c_int, _P, c_int, c_int, c_int, _P, _P, _P, c_int, _P, _P, _P, _P, _P], c_int),
     'cosyb200_refine_n': ([_P, c_int, c_int, c_int, _P, c_int, c_int, c_int, _P, _P, _P, _P, c_int, _P,
                            _P, _P, _P, _P, _P, _P], c_int),
+    'cosyb200_set_option': ([_P, c_char_p, c_int], c_int),
+    'cosyb200_debug_pointwise': ([_P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, c_int, _P, c_int, _P, _P], c_int),
+    'cosyb200_debug_trace': ([_P, _P], c_int),
     'cosyb200_profile_enable': ([_P, c_int], c_int),
     'cosyb200_profile_read': ([_P, c_int, _P, _P], c_int),
     'cosyb200_ransac_infos': ([c_int, _P, _P, c_int, c_int, POINTER(c_int64), POINTER(c_int64), _P, _P], c_int),

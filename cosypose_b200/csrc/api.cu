@@ -11,6 +11,7 @@
 #include "kernels_geometry.cuh"
 #include "kernels_ransac.cuh"
 #include "kernels_ba.cuh"
+#include "kernels_tc.cuh"
 
 namespace cosyb {
 
@@ -99,6 +100,47 @@ static void launch_gemm(bool gate, bool swish, bool resid, const float* A, const
   else launch_gemm_tile<128, 128, 8, 8>(gate, swish, resid, A, Wkn, bias, g, r, C, M, N, K, rows_per_img, st);
 }
 
+// tensor-core path: Wpk = tc::pack_weights image of the [N][K] weight
+template <int BN_MAX, bool G, bool S, bool R>
+static int launch_gemm_tc_inst(const tc::Plan& p, const float* A, const float* Wpk, const float* bias, const float* g,
+                               const float* r, float* C, int M, int N, int K, int rows_per_img, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    CB_CUDA(cudaFuncSetAttribute(tc::k_pw_gemm_tc<BN_MAX, G, S, R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 225 * 1024));
+    attr_set = true;
+  }
+  static int n_sms = 0;
+  if (n_sms == 0) {
+    int dev = 0;
+    CB_CUDA(cudaGetDevice(&dev));
+    CB_CUDA(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int m_tiles = (M + tc::BM - 1) / tc::BM;
+  const int grid = std::min(m_tiles, std::max(1, n_sms / p.n_tiles)) * p.n_tiles;   // multiple of n_tiles
+  tc::k_pw_gemm_tc<BN_MAX, G, S, R><<<grid, tc::THREADS, p.smem_bytes, st>>>(A, Wpk, bias, g, r, C, M, N, K,
+                                                                             rows_per_img, p.bn, p.n_tiles, p.nb,
+                                                                             p.resident);
+  CB_LAUNCH_CHECK();
+  return 0;
+}
+
+static int launch_gemm_tc(bool gate, bool swish, bool resid, const float* A, const float* Wpk, const float* bias,
+                          const float* g, const float* r, float* C, int M, int N, int K, int rows_per_img,
+                          cudaStream_t st) {
+  const tc::Plan p = tc::make_plan(N, K);
+#define TC_ARGS p, A, Wpk, bias, g, r, C, M, N, K, rows_per_img, st
+#define TC_DISPATCH(G, S, R) launch_gemm_tc_inst<64, G, S, R>(TC_ARGS)
+  if (!gate && swish && !resid) return TC_DISPATCH(false, true, false);
+  if (gate && !swish && !resid) return TC_DISPATCH(true, false, false);
+  if (gate && !swish && resid) return TC_DISPATCH(true, false, true);
+  if (!gate && !swish && !resid) return TC_DISPATCH(false, false, false);
+#undef TC_DISPATCH
+#undef TC_ARGS
+  set_error("launch_gemm_tc: unsupported epilogue");
+  return COSYB200_EINVAL;
+}
+
 // ---- depthwise dispatch ---------------------------------------------------------------------
 struct DwPlan { int n_chunks, Gc, P, pix_per_tile, tiles; int V, TH, tiles_x; bool rolling; };
 static DwPlan dw_plan(const BlockSpec& b) {
@@ -181,6 +223,10 @@ static int net_forward(cosyb200_handle* h, int slot, int B, const float* crops, 
     const float* dw_in = x;
     if (b.e != 1) {
       LaunchScope ls(h, CAT_EXPAND, st);
+      if (h->gemm_impl == 1) {
+        if (int rc2 = launch_gemm_tc(false, true, false, x, w.expand_tc, w.expand_bias, nullptr, nullptr, h->buf_e,
+                                     Min, b.cexp, b.cin, 1, st)) return rc2;
+      } else
       launch_gemm(false, true, false, x, w.expand_kn, w.expand_bias, nullptr, nullptr, h->buf_e, Min,
                   b.cexp, b.cin, 1, st);
       CB_LAUNCH_CHECK();
@@ -201,6 +247,10 @@ static int net_forward(cosyb200_handle* h, int slot, int B, const float* crops, 
     CB_LAUNCH_CHECK();
     {
       LaunchScope ls(h, CAT_PROJECT, st);
+      if (h->gemm_impl == 1) {
+        if (int rc2 = launch_gemm_tc(true, false, b.skip != 0, h->buf_d, w.proj_tc, w.proj_bias, h->gate, x, y, Mout,
+                                     b.cout, b.cexp, b.hout * b.wout, st)) return rc2;
+      } else
       launch_gemm(true, false, b.skip != 0, h->buf_d, w.proj_kn, w.proj_bias, h->gate, x, y, Mout, b.cout,
                   b.cexp, b.hout * b.wout, st);
     }
@@ -213,6 +263,10 @@ static int net_forward(cosyb200_handle* h, int slot, int B, const float* crops, 
   const int n_pos = last.hout * last.wout;
   {
     LaunchScope ls(h, CAT_HEAD, st);
+    if (h->gemm_impl == 1) {
+      if (int rc2 = launch_gemm_tc(false, true, false, h->act[cur], m.head_tc, m.head_bias, nullptr, nullptr, h->buf_e,
+                                   B * n_pos, N_FEATURES, last.cout, 1, st)) return rc2;
+    } else
     launch_gemm(false, true, false, h->act[cur], m.head_kn, m.head_bias, nullptr, nullptr, h->buf_e,
                 B * n_pos, N_FEATURES, last.cout, 1, st);
   }
@@ -380,6 +434,7 @@ int cosyb200_load_pose_model(cosyb200_handle* h, int slot, int n, const char* co
       pack_pw(W, b.cexp, b.cin, scale, nk, kn);
       rc |= upload(m, &w.expand_nk, nk);
       rc |= upload(m, &w.expand_kn, kn);
+      rc |= upload(m, &w.expand_tc, tc::pack_weights(nk.data(), b.cexp, b.cin));
       rc |= upload(m, &w.expand_bias, shift);
     }
     {
@@ -411,6 +466,7 @@ int cosyb200_load_pose_model(cosyb200_handle* h, int slot, int n, const char* co
       pack_pw(W, b.cout, b.cexp, scale, nk, kn);
       rc |= upload(m, &w.proj_nk, nk);
       rc |= upload(m, &w.proj_kn, kn);
+      rc |= upload(m, &w.proj_tc, tc::pack_weights(nk.data(), b.cout, b.cexp));
       rc |= upload(m, &w.proj_bias, shift);
     }
   }
@@ -421,6 +477,7 @@ int cosyb200_load_pose_model(cosyb200_handle* h, int slot, int n, const char* co
     pack_pw(W, N_FEATURES, cin, scale, nk, kn);
     rc |= upload(m, &m.head_nk, nk);
     rc |= upload(m, &m.head_kn, kn);
+    rc |= upload(m, &m.head_tc, tc::pack_weights(nk.data(), N_FEATURES, cin));
     rc |= upload(m, &m.head_bias, shift);
     const float* fw = get("pose_fc.weight", (int64_t)POSE_DIM * N_FEATURES);
     const float* fb = get("pose_fc.bias", POSE_DIM);
@@ -576,6 +633,60 @@ int cosyb200_refine_n(cosyb200_handle* h, int slot, int B, int n_iter, const flo
                               TCO_out + (size_t)n * B * 16, stream);
     if (rc) return rc;
   }
+  return COSYB200_OK;
+}
+
+int cosyb200_set_option(cosyb200_handle* h, const char* name, int value) {
+  CB_CHECK_ARG(h != nullptr && name != nullptr, "set_option: bad arguments");
+  if (strcmp(name, "gemm_impl") == 0) {
+    CB_CHECK_ARG(value == 0 || value == 1, "set_option: gemm_impl must be 0 (cuda cores) or 1 (tcgen05)");
+    h->gemm_impl = value;
+    return COSYB200_OK;
+  }
+  set_error("set_option: unknown option %s", name);
+  return COSYB200_EINVAL;
+}
+
+int cosyb200_debug_pointwise(cosyb200_handle* h, int impl, int M, int N, int K, const float* A,
+                             const float* W_nk_host, const float* bias_host, const float* gate,
+                             int rows_per_img, const float* resid, int swish, float* C, void* stream) {
+  CB_CHECK_ARG(h != nullptr && M >= 1 && N >= 8 && K >= 8 && N % 8 == 0 && K % 8 == 0, "debug_pointwise: bad sizes");
+  CB_CHECK_ARG(A && W_nk_host && bias_host && C, "debug_pointwise: null pointer");
+  DeviceGuard guard(h->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  std::vector<float> w;
+  if (impl == 1) {
+    w = tc::pack_weights(W_nk_host, N, K);
+  } else {
+    w.resize((size_t)N * K);
+    for (int n = 0; n < N; ++n)
+      for (int k = 0; k < K; ++k) w[(size_t)k * N + n] = W_nk_host[(size_t)n * K + k];
+  }
+  float *dW = nullptr, *dB = nullptr;
+  CB_CUDA(cudaMalloc((void**)&dW, w.size() * 4));
+  CB_CUDA(cudaMalloc((void**)&dB, (size_t)N * 4));
+  CB_CUDA(cudaMemcpy(dW, w.data(), w.size() * 4, cudaMemcpyHostToDevice));
+  CB_CUDA(cudaMemcpy(dB, bias_host, (size_t)N * 4, cudaMemcpyHostToDevice));
+  int rc = 0;
+  {
+    LaunchScope ls(h, CAT_EXPAND, st);
+    if (impl == 1) rc = launch_gemm_tc(gate != nullptr, swish != 0, resid != nullptr, A, dW, dB, gate, resid, C, M, N, K,
+                                       rows_per_img, st);
+    else launch_gemm(gate != nullptr, swish != 0, resid != nullptr, A, dW, dB, gate, resid, C, M, N, K, rows_per_img, st);
+  }
+  cudaError_t e = cudaStreamSynchronize(st);
+  cudaFree(dW);
+  cudaFree(dB);
+  if (rc) return rc;
+  if (e != cudaSuccess) { set_error("debug_pointwise: %s", cudaGetErrorString(e)); return COSYB200_ECUDA; }
+  CB_LAUNCH_CHECK();
+  return COSYB200_OK;
+}
+
+int cosyb200_debug_trace(cosyb200_handle* h, long long* trace_dev) {
+  CB_CHECK_ARG(h != nullptr, "debug_trace: null handle");
+  DeviceGuard guard(h->device);
+  CB_CUDA(cudaMemcpyToSymbol(tc::g_trace, &trace_dev, sizeof(trace_dev)));
   return COSYB200_OK;
 }
 

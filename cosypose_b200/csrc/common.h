@@ -61,6 +61,8 @@ struct BlockWeights {
   float* proj_nk = nullptr;     // [cout][cexp]
   float* proj_kn = nullptr;     // [cexp][cout]
   float* proj_bias = nullptr;   // [cout]
+  float* expand_tc = nullptr;   // tensor-core image of expand_nk (kernels_tc.cuh pack_weights)
+  float* proj_tc = nullptr;     // tensor-core image of proj_nk
 };
 
 struct PoseModel {
@@ -71,6 +73,7 @@ struct PoseModel {
   float* head_nk = nullptr;    // [1536][384]
   float* head_kn = nullptr;    // [384][1536]
   float* head_bias = nullptr;  // [1536]
+  float* head_tc = nullptr;    // tensor-core image of head_nk
   float* fc_w = nullptr;       // [9][1536]
   float* fc_b = nullptr;       // [9]
   std::vector<void*> allocs;
@@ -104,6 +107,7 @@ struct cosyb200_handle {
   int64_t launches[N_CAT] = {0};
   double cat_ms[N_CAT] = {0};
   bool profiling = false;
+  int gemm_impl = 1;   // 1x1 convolutions: 0 = CUDA-core fp32 kernel, 1 = tcgen05 3xTF32 kernel
   std::vector<cudaEvent_t> ev_pool;   // pairs: [2*i] start, [2*i+1] stop
   std::vector<int> ev_cat;            // category of each recorded pair
   cudaStream_t ev_stream = nullptr;

@@ -206,6 +206,27 @@ class Engine:
             _ptr(out['boxes_crop']), _ptr(out['pose']), self._stream()), 'refine_n')
         return out
 
+    def set_option(self, name, value):
+        _lib.check(self._L.cosyb200_set_option(self._h, name.encode(), int(value)), 'set_option')
+
+    def debug_pointwise(self, impl, A, W_nk, bias, gate=None, rows_per_img=1, resid=None, swish=False):
+        """One 1x1 convolution C = act((A*gate) @ W^T + bias) (+ resid); impl 0 = CUDA cores, 1 = tcgen05."""
+        M, K = A.shape
+        N = W_nk.shape[0]
+        self._chk(A, torch.float32, (M, K), 'A')
+        W = np.ascontiguousarray(W_nk.detach().cpu().numpy() if isinstance(W_nk, torch.Tensor) else W_nk, dtype=np.float32)
+        b = np.ascontiguousarray(bias.detach().cpu().numpy() if isinstance(bias, torch.Tensor) else bias, dtype=np.float32)
+        assert W.shape == (N, K) and b.shape == (N,)
+        if gate is not None:
+            self._chk(gate, torch.float32, (-(-M // rows_per_img), K), 'gate')
+        if resid is not None:
+            self._chk(resid, torch.float32, (M, N), 'resid')
+        C = self._new(M, N)
+        _lib.check(self._L.cosyb200_debug_pointwise(self._h, int(impl), M, N, K, _ptr(A), _np_ptr(W), _np_ptr(b),
+                                                    _ptr(gate), int(rows_per_img), _ptr(resid), int(swish), _ptr(C),
+                                                    self._stream()), 'debug_pointwise')
+        return C
+
     # -- launch accounting --------------------------------------------------------------------
     CATEGORIES = ('geometry', 'roi_crop', 'stem', 'expand_1x1', 'depthwise', 'squeeze_excite',
                   'project_1x1', 'head_1x1', 'pool_fc_update', 'ransac')

@@ -129,6 +129,23 @@ int cosyb200_refine_n(cosyb200_handle* h, int slot, int B, int n_iter, const flo
                       int render_u8, const float* TCO_in_dev, float* TCO_out_dev, float* K_crop_dev,
                       float* boxes_rend_dev, float* boxes_crop_dev, float* pose9_dev, void* stream);
 
+/* Engine options.  "gemm_impl": 1 (default) runs the 1x1 convolutions on the tcgen05 tensor cores
+ * with the 3xTF32 split, 0 on CUDA cores in plain fp32 (kept as the per-block parity anchor). */
+int cosyb200_set_option(cosyb200_handle* h, const char* name, int value);
+
+/* One 1x1 convolution on caller data, for kernel-level tests (reference: the Conv2d 1x1 + folded
+ * BatchNorm (+ swish) of models/efficientnet.py:80-81,90,188):
+ *   C[M,N] = act((A[M,K] * gate[m / rows_per_img, k]) @ W[N,K]^T + bias[N]) (+ resid[M,N])
+ * A, gate (may be NULL), resid (may be NULL), C on the device; W, bias on the host.  Synchronises. */
+int cosyb200_debug_pointwise(cosyb200_handle* h, int impl, int M, int N, int K, const float* A_dev,
+                             const float* W_nk_host, const float* bias_host, const float* gate_dev,
+                             int rows_per_img, const float* resid_dev, int swish, float* C_dev,
+                             void* stream);
+
+/* Tuning aid: when trace_dev (32 int64 slots, device memory) is non-NULL, CTA (0,0) of the tensor-core
+ * 1x1 kernel stores clock64() stamps of its pipeline events there; NULL switches it off. */
+int cosyb200_debug_trace(cosyb200_handle* h, long long* trace_dev);
+
 /* Launch accounting (no reference counterpart; the reference times with a wall-clock Timer,
  * utils/timer.py:4-36).  Every kernel the engine launches is counted per category:
  *   0 geometry, 1 roi crop, 2 stem, 3 expand 1x1, 4 depthwise, 5 squeeze-excite, 6 project 1x1,
