@@ -107,7 +107,7 @@ static int launch_gemm_tc_inst(const tc::Plan& p, const float* A, const float* W
   static bool attr_set = false;
   if (!attr_set) {
     CB_CUDA(cudaFuncSetAttribute(tc::k_pw_gemm_tc<BN_MAX, G, S, R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 225 * 1024));
+                                 112 * 1024));
     attr_set = true;
   }
   static int n_sms = 0;
@@ -117,7 +117,7 @@ static int launch_gemm_tc_inst(const tc::Plan& p, const float* A, const float* W
     CB_CUDA(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   const int m_tiles = (M + tc::BM - 1) / tc::BM;
-  const int grid = std::min(m_tiles, std::max(1, n_sms / p.n_tiles)) * p.n_tiles;   // multiple of n_tiles
+  const int grid = std::min(m_tiles, std::max(1, 2 * n_sms / p.n_tiles)) * p.n_tiles;   // multiple of n_tiles, 2 CTAs / SM
   tc::k_pw_gemm_tc<BN_MAX, G, S, R><<<grid, tc::THREADS, p.smem_bytes, st>>>(A, Wpk, bias, g, r, C, M, N, K,
                                                                              rows_per_img, p.bn, p.n_tiles, p.nb,
                                                                              p.resident);
@@ -142,31 +142,19 @@ static int launch_gemm_tc(bool gate, bool swish, bool resid, const float* A, con
 }
 
 // ---- depthwise dispatch ---------------------------------------------------------------------
-struct DwPlan { int n_chunks, Gc, P, pix_per_tile, tiles; int V, TH, tiles_x; bool rolling; };
+struct DwPlan { int n_chunks, Gc, P, tiles; int V, TH, tiles_x; };
 static DwPlan dw_plan(const BlockSpec& b) {
+  // k_dwconv_roll: thread = (channel vector, output column), rolls down TH output rows
   DwPlan p;
-  p.rolling = b.s == 1;
-  if (p.rolling) {   // k_dwconv_s1: thread = (channel vector, output column), rolls down TH rows
-    p.V = b.k == 3 ? 4 : 2;
-    int G = b.cexp / p.V;
-    p.n_chunks = (G + DW_MAX_THREADS - 1) / DW_MAX_THREADS;
-    while (G % p.n_chunks) ++p.n_chunks;
-    p.Gc = G / p.n_chunks;
-    p.P = DW_MAX_THREADS / p.Gc;
-    p.TH = std::min(b.hout, 30);
-    p.tiles_x = (b.wout + p.P - 1) / p.P;
-    p.tiles = p.tiles_x * ((b.hout + p.TH - 1) / p.TH);
-    p.pix_per_tile = p.P * p.TH;
-    return p;
-  }
-  p.V = 4; p.TH = 0; p.tiles_x = 0;
-  int G = b.cexp / 4;
+  p.V = b.k == 3 ? 4 : 2;
+  int G = b.cexp / p.V;
   p.n_chunks = (G + DW_MAX_THREADS - 1) / DW_MAX_THREADS;
   while (G % p.n_chunks) ++p.n_chunks;
   p.Gc = G / p.n_chunks;
   p.P = DW_MAX_THREADS / p.Gc;
-  p.pix_per_tile = 128;
-  p.tiles = (b.hout * b.wout + p.pix_per_tile - 1) / p.pix_per_tile;
+  p.TH = std::min(b.hout, 30);
+  p.tiles_x = (b.wout + p.P - 1) / p.P;
+  p.tiles = p.tiles_x * ((b.hout + p.TH - 1) / p.TH);
   return p;
 }
 
@@ -175,20 +163,11 @@ static int launch_dw(const BlockSpec& b, const BlockWeights& w, const float* in,
   DwPlan p = dw_plan(b);
   dim3 grid(p.tiles, p.n_chunks, B);
   int threads = p.Gc * p.P;
-  if (p.rolling) {
-#define DW1_ARGS in, w.dw_w, w.dw_bias, out, partial, b.hin, b.win, b.cexp, b.pad_lo, p.Gc, p.P, p.TH, p.tiles_x, p.tiles
-    if (b.k == 3) k_dwconv_s1<3, 4><<<grid, threads, 0, st>>>(DW1_ARGS);
-    else if (b.k == 5) k_dwconv_s1<5, 2><<<grid, threads, 0, st>>>(DW1_ARGS);
-    else { set_error("unsupported depthwise k=%d", b.k); return COSYB200_EINVAL; }
-#undef DW1_ARGS
-    CB_LAUNCH_CHECK();
-    return 0;
-  }
-#define DW_ARGS in, w.dw_w, w.dw_bias, out, partial, b.hin, b.win, b.cexp, b.hout, b.wout, b.pad_lo, p.Gc, p.P, p.pix_per_tile, p.tiles
-  if (b.k == 3 && b.s == 1) k_dwconv<3, 1><<<grid, threads, 0, st>>>(DW_ARGS);
-  else if (b.k == 3 && b.s == 2) k_dwconv<3, 2><<<grid, threads, 0, st>>>(DW_ARGS);
-  else if (b.k == 5 && b.s == 1) k_dwconv<5, 1><<<grid, threads, 0, st>>>(DW_ARGS);
-  else if (b.k == 5 && b.s == 2) k_dwconv<5, 2><<<grid, threads, 0, st>>>(DW_ARGS);
+#define DW_ARGS in, w.dw_w, w.dw_bias, out, partial, b.hin, b.win, b.cexp, b.hout, b.wout, b.pad_lo, p.Gc, p.P, p.TH, p.tiles_x, p.tiles
+  if (b.k == 3 && b.s == 1) k_dwconv_roll<3, 1, 4><<<grid, threads, 0, st>>>(DW_ARGS);
+  else if (b.k == 3 && b.s == 2) k_dwconv_roll<3, 2, 4><<<grid, threads, 0, st>>>(DW_ARGS);
+  else if (b.k == 5 && b.s == 1) k_dwconv_roll<5, 1, 2><<<grid, threads, 0, st>>>(DW_ARGS);
+  else if (b.k == 5 && b.s == 2) k_dwconv_roll<5, 2, 2><<<grid, threads, 0, st>>>(DW_ARGS);
   else { set_error("unsupported depthwise k=%d s=%d", b.k, b.s); return COSYB200_EINVAL; }
 #undef DW_ARGS
   CB_LAUNCH_CHECK();
@@ -240,9 +219,16 @@ static int net_forward(cosyb200_handle* h, int slot, int B, const float* crops, 
     DwPlan p = dw_plan(b);
     {
       LaunchScope ls(h, CAT_SE, st);
-      k_se_gate<<<B, SE_THREADS, 0, st>>>(h->pool_partial, p.tiles, b.cexp, b.cse,
-                                          1.0f / float(b.hout * b.wout), w.se_r_w, w.se_r_b, w.se_e_w,
-                                          w.se_e_b, h->gate);
+      static bool se_attr = false;
+      if (!se_attr) {
+        CB_CUDA(cudaFuncSetAttribute(k_se_gate, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        se_attr = true;
+      }
+      const dim3 se_grid((B + SE_IMGS - 1) / SE_IMGS, b.cexp >= 1024 ? 8 : (b.cexp >= 256 ? 4 : 1));
+      const size_t se_smem = (size_t)SE_IMGS * (b.cexp + b.cse) * sizeof(float);
+      k_se_gate<<<se_grid, SE_THREADS, se_smem, st>>>(B, h->pool_partial, p.tiles, b.cexp, b.cse,
+                                                      1.0f / float(b.hout * b.wout), w.se_r_w, w.se_r_b, w.se_e_w,
+                                                      w.se_e_b, h->gate);
     }
     CB_LAUNCH_CHECK();
     {
@@ -457,7 +443,14 @@ int cosyb200_load_pose_model(cosyb200_handle* h, int slot, int n, const char* co
       };
       copy_up(p + "._se_reduce.weight", (int64_t)b.cse * b.cexp, &w.se_r_w);
       copy_up(p + "._se_reduce.bias", b.cse, &w.se_r_b);
-      copy_up(p + "._se_expand.weight", (int64_t)b.cexp * b.cse, &w.se_e_w);
+      {   // expand weight transposed to [cse][cexp]
+        const float* src = get(p + "._se_expand.weight", (int64_t)b.cexp * b.cse);
+        tmp.assign((size_t)b.cexp * b.cse, 0.f);
+        if (src)
+          for (int c = 0; c < b.cexp; ++c)
+            for (int j = 0; j < b.cse; ++j) tmp[(size_t)j * b.cexp + c] = src[(size_t)c * b.cse + j];
+        rc |= upload(m, &w.se_e_w, tmp);
+      }
       copy_up(p + "._se_expand.bias", b.cexp, &w.se_e_b);
     }
     {

@@ -56,7 +56,7 @@ struct BlockWeights {
   float* dw_bias = nullptr;     // [cexp]
   float* se_r_w = nullptr;      // [cse][cexp]
   float* se_r_b = nullptr;      // [cse]
-  float* se_e_w = nullptr;      // [cexp][cse]
+  float* se_e_w = nullptr;      // [cse][cexp] (transposed at load)
   float* se_e_b = nullptr;      // [cexp]
   float* proj_nk = nullptr;     // [cout][cexp]
   float* proj_kn = nullptr;     // [cexp][cout]

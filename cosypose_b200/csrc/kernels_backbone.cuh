@@ -296,10 +296,11 @@ k_dwconv(const float* __restrict__ in, const float* __restrict__ w /*[KS*KS][C]*
   }
 }
 
-// Stride-1 depthwise with a rolling window: a thread owns (channel vector, output column) and walks
-// down TH output rows.  Each input row is loaded once per thread (KS vector loads, horizontally
-// shared through L1) and accumulated into the KS output rows it touches, held in a register ring;
-// the KS*KS taps of the thread's channels stay in registers.  Loads per output drop from KS^2 to ~KS.
+// Depthwise with a rolling window (stride 1 or 2): a thread owns (channel vector, output column) and
+// walks down TH output rows.  Each input row is loaded once per thread (KS vector loads, horizontally
+// shared through L1) and accumulated into the ceil(KS/S) output rows it touches, held in a register
+// ring; the KS*KS taps of the thread's channels stay in registers.  Loads per output drop from KS^2
+// to ~KS*S.
 //   grid = (tiles_x * tiles_y, n_chunks, B); block = Gc * PX threads
 template <int V> struct VecT;
 template <> struct VecT<4> { using T = float4; };
@@ -311,12 +312,15 @@ template <int V> __device__ __forceinline__ void vzero(float* a) {
   for (int i = 0; i < V; ++i) a[i] = 0.f;
 }
 
-template <int KS, int V>
+template <int KS, int S, int V>
 __global__ void __launch_bounds__(DW_MAX_THREADS)
-k_dwconv_s1(const float* __restrict__ in, const float* __restrict__ w /*[KS*KS][C]*/,
-            const float* __restrict__ bias, float* __restrict__ out, float* __restrict__ partial,
-            int H, int W, int C, int pad, int Gc, int PX, int TH, int tiles_x, int tiles_per_img) {
+k_dwconv_roll(const float* __restrict__ in, const float* __restrict__ w /*[KS*KS][C]*/,
+              const float* __restrict__ bias, float* __restrict__ out, float* __restrict__ partial,
+              int H, int W, int C, int Ho, int Wo, int pad, int Gc, int PX, int TH, int tiles_x,
+              int tiles_per_img) {
   using VT = typename VecT<V>::T;
+  constexpr int NSLOT = (KS + S - 1) / S;      // output rows in flight per thread
+  constexpr int PERIOD = S * NSLOT;            // the (input row -> slot, tap row) pattern repeats with this period
   __shared__ float sred[DW_MAX_THREADS * V];
   const int b = blockIdx.z, tile = blockIdx.x;
   const int tile_x = tile % tiles_x, tile_y = tile / tiles_x;
@@ -324,9 +328,9 @@ k_dwconv_s1(const float* __restrict__ in, const float* __restrict__ w /*[KS*KS][
   const int c = (blockIdx.y * Gc + tid % Gc) * V;
   const int ox = tile_x * PX + tid / Gc;
   const int oy0 = tile_y * TH;
-  const bool col_ok = ox < W;
+  const bool col_ok = ox < Wo;
   const float* inb = in + (size_t)b * H * W * C + c;
-  float* outb = out + (size_t)b * H * W * C + c;
+  float* outb = out + (size_t)b * Ho * Wo * C + c;
 
   float wreg[KS * KS][V];
 #pragma unroll
@@ -343,23 +347,26 @@ k_dwconv_s1(const float* __restrict__ in, const float* __restrict__ w /*[KS*KS][
 #pragma unroll
     for (int i = 0; i < V; ++i) bv[i] = tp[i];
   }
-  float acc[KS][V];
+  float acc[NSLOT][V];
 #pragma unroll
-  for (int s = 0; s < KS; ++s) vzero<V>(acc[s]);
+  for (int s = 0; s < NSLOT; ++s) vzero<V>(acc[s]);
   float psum[V];
   vzero<V>(psum);
 
-  const int n_in_rows = TH + KS - 1;
-  for (int r0 = 0; r0 < n_in_rows; r0 += KS) {
+  // input rows r = 0 .. (TH-1)*S + KS - 1 relative to iy0 = oy0*S - pad; input row r feeds output row
+  // (r - ky) / S with tap row ky whenever that division is exact.
+  const int n_in_rows = (TH - 1) * S + KS;
+  const int iy0 = oy0 * S - pad, ix0 = ox * S - pad;
+  for (int r0 = 0; r0 < n_in_rows; r0 += PERIOD) {
 #pragma unroll
-    for (int j = 0; j < KS; ++j) {
+    for (int j = 0; j < PERIOD; ++j) {
       const int r = r0 + j;
-      const int iy = oy0 - pad + r;
+      const int iy = iy0 + r;
       if (r < n_in_rows && iy >= 0 && iy < H && col_ok) {
         float v[KS][V];
 #pragma unroll
         for (int kx = 0; kx < KS; ++kx) {
-          const int ix = ox - pad + kx;
+          const int ix = ix0 + kx;
           if (ix >= 0 && ix < W) {
             VT t = *reinterpret_cast<const VT*>(inb + ((size_t)iy * W + ix) * C);
             const float* tp = reinterpret_cast<const float*>(&t);
@@ -369,29 +376,33 @@ k_dwconv_s1(const float* __restrict__ in, const float* __restrict__ w /*[KS*KS][
             vzero<V>(v[kx]);
           }
         }
-        // input row r feeds output row (r - ky) with tap row ky; ring slot (j - ky) mod KS
 #pragma unroll
         for (int ky = 0; ky < KS; ++ky) {
-          const int slot = (j - ky + KS) % KS;
+          if ((j - ky + PERIOD * KS) % S == 0) {
+            const int slot = ((j - ky + PERIOD * KS) / S) % NSLOT;
 #pragma unroll
-          for (int kx = 0; kx < KS; ++kx)
+            for (int kx = 0; kx < KS; ++kx)
 #pragma unroll
-            for (int i = 0; i < V; ++i) acc[slot][i] = fmaf(v[kx][i], wreg[ky * KS + kx][i], acc[slot][i]);
+              for (int i = 0; i < V; ++i) acc[slot][i] = fmaf(v[kx][i], wreg[ky * KS + kx][i], acc[slot][i]);
+          }
         }
       }
-      // output row (r - KS + 1) has now seen all of its input rows
-      const int slot_done = (j + 1) % KS;
-      const int oyr = r - (KS - 1);
-      if (oyr >= 0 && oyr < TH && oy0 + oyr < H && col_ok) {
-        float o[V];
+      // output row (r - KS + 1) / S has now seen all of its input rows
+      if ((j - (KS - 1) + PERIOD * KS) % S == 0) {
+        const int slot_done = ((j - (KS - 1) + PERIOD * KS) / S) % NSLOT;
+        const int num = r - (KS - 1);
+        const int oyr = num >= 0 ? num / S : -1;
+        if (oyr >= 0 && oyr < TH && oy0 + oyr < Ho && col_ok) {
+          float o[V];
 #pragma unroll
-        for (int i = 0; i < V; ++i) {
-          o[i] = swishf(acc[slot_done][i] + bv[i]);
-          psum[i] += o[i];
+          for (int i = 0; i < V; ++i) {
+            o[i] = swishf(acc[slot_done][i] + bv[i]);
+            psum[i] += o[i];
+          }
+          *reinterpret_cast<VT*>(outb + ((size_t)(oy0 + oyr) * Wo + ox) * C) = pack_vec(o);
         }
-        *reinterpret_cast<VT*>(outb + ((size_t)(oy0 + oyr) * W + ox) * C) = pack_vec(o);
+        vzero<V>(acc[slot_done]);
       }
-      vzero<V>(acc[slot_done]);
     }
   }
 #pragma unroll
@@ -410,39 +421,76 @@ k_dwconv_s1(const float* __restrict__ in, const float* __restrict__ w /*[KS*KS][
 
 // -------------------------------------------------------------------------------- squeeze-excite
 // gate[b][c] = sigmoid(be[c] + sum_j We[c][j] * swish(br[j] + sum_c' Wr[j][c'] * mean[c']))
-// (reference: models/efficientnet.py:85-88).  One CTA per hypothesis.
-constexpr int SE_THREADS = 256;
-constexpr int SE_MAX_C = 2304, SE_MAX_R = 96;
+// (reference: models/efficientnet.py:85-88).  grid = (ceil(B / SE_IMGS), n_split): a CTA serves SE_IMGS
+// hypotheses so that each weight element it reads from L2 is used SE_IMGS times; every CTA rebuilds the
+// channel means and the reduced vectors (cheap), then produces its slice of the gates.  `we_t` is the
+// expand weight transposed to [Cse][C] so that the last stage reads contiguously.
+// dynamic smem: SE_IMGS * (C + Cse) floats.
+constexpr int SE_THREADS = 1024;
+constexpr int SE_IMGS = 8;
 
 __global__ void __launch_bounds__(SE_THREADS)
-k_se_gate(const float* __restrict__ partial, int tiles_per_img, int C, int Cse, float inv_hw,
-          const float* __restrict__ wr, const float* __restrict__ br, const float* __restrict__ we,
+k_se_gate(int B, const float* __restrict__ partial, int tiles_per_img, int C, int Cse, float inv_hw,
+          const float* __restrict__ wr, const float* __restrict__ br, const float* __restrict__ we_t,
           const float* __restrict__ be, float* __restrict__ gate) {
-  __shared__ float s_mean[SE_MAX_C];
-  __shared__ float s_r[SE_MAX_R];
-  const int b = blockIdx.x, tid = threadIdx.x;
-  const float* pb = partial + (size_t)b * tiles_per_img * C;
-  for (int c = tid; c < C; c += SE_THREADS) {
+  extern __shared__ float se_smem[];
+  float* s_mean = se_smem;                 // [SE_IMGS][C]
+  float* s_r = se_smem + SE_IMGS * C;      // [SE_IMGS][Cse]
+  const int b0 = blockIdx.x * SE_IMGS, tid = threadIdx.x;
+  const int n_img = min(SE_IMGS, B - b0);
+  for (int i = tid; i < SE_IMGS * C; i += SE_THREADS) {
+    const int im = i / C, c = i % C;
     float s = 0.f;
-    for (int t = 0; t < tiles_per_img; ++t) s += pb[(size_t)t * C + c];
-    s_mean[c] = s * inv_hw;
+    if (im < n_img) {
+      const float* pb = partial + ((size_t)(b0 + im) * tiles_per_img) * C + c;
+      int t = 0;
+      for (; t + 4 <= tiles_per_img; t += 4) {      // independent loads in flight, fixed summation order
+        const float v0 = pb[(size_t)t * C], v1 = pb[(size_t)(t + 1) * C], v2 = pb[(size_t)(t + 2) * C], v3 = pb[(size_t)(t + 3) * C];
+        s += v0; s += v1; s += v2; s += v3;
+      }
+      for (; t < tiles_per_img; ++t) s += pb[(size_t)t * C];
+    }
+    s_mean[i] = s * inv_hw;
   }
   __syncthreads();
   const int warp = tid / 32, lane = tid % 32;
   for (int j = warp; j < Cse; j += SE_THREADS / 32) {
     const float* wrow = wr + (size_t)j * C;
-    float s = 0.f;
-    for (int c = lane; c < C; c += 32) s = fmaf(__ldg(wrow + c), s_mean[c], s);
+    float acc[SE_IMGS];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) s_r[j] = swishf(s + __ldg(br + j));
+    for (int im = 0; im < SE_IMGS; ++im) acc[im] = 0.f;
+    for (int c = lane * 4; c < C; c += 128) {   // C is a multiple of 8
+      const float4 wv = __ldg(reinterpret_cast<const float4*>(wrow + c));
+#pragma unroll
+      for (int im = 0; im < SE_IMGS; ++im) {
+        const float4 mv = *reinterpret_cast<const float4*>(s_mean + im * C + c);
+        acc[im] = fmaf(wv.x, mv.x, fmaf(wv.y, mv.y, fmaf(wv.z, mv.z, fmaf(wv.w, mv.w, acc[im]))));
+      }
+    }
+#pragma unroll
+    for (int im = 0; im < SE_IMGS; ++im) {
+      float s = acc[im];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == 0) s_r[im * Cse + j] = swishf(s + __ldg(br + j));
+    }
   }
   __syncthreads();
-  for (int c = tid; c < C; c += SE_THREADS) {
-    const float* wrow = we + (size_t)c * Cse;
-    float s = __ldg(be + c);
-    for (int j = 0; j < Cse; ++j) s = fmaf(__ldg(wrow + j), s_r[j], s);
-    gate[(size_t)b * C + c] = sigmoidf_(s);
+  const int per = (C + gridDim.y - 1) / gridDim.y;
+  const int c_end = min(C, (int)(blockIdx.y + 1) * per);
+  for (int c = blockIdx.y * per + tid; c < c_end; c += SE_THREADS) {
+    float acc[SE_IMGS];
+    const float bias = __ldg(be + c);
+#pragma unroll
+    for (int im = 0; im < SE_IMGS; ++im) acc[im] = bias;
+    for (int j = 0; j < Cse; ++j) {
+      const float wv = __ldg(we_t + (size_t)j * C + c);
+#pragma unroll
+      for (int im = 0; im < SE_IMGS; ++im) acc[im] = fmaf(wv, s_r[im * Cse + j], acc[im]);
+    }
+#pragma unroll
+    for (int im = 0; im < SE_IMGS; ++im)
+      if (im < n_img) gate[(size_t)(b0 + im) * C + c] = sigmoidf_(acc[im]);
   }
 }
 

@@ -38,8 +38,8 @@ constexpr int BK = 32;            // fp32 elements per k-stage (8 core-matrix co
 constexpr int UMMA_K = 8;         // tf32
 constexpr int KSTEPS = BK / UMMA_K;
 constexpr int PRODUCER_THREADS = 128;
-constexpr int DRAIN_THREADS = 256;
-constexpr int THREADS = 2 * PRODUCER_THREADS + 32 + DRAIN_THREADS + 32;   // 18 warps
+constexpr int DRAIN_THREADS = 128;
+constexpr int THREADS = PRODUCER_THREADS + 32 + DRAIN_THREADS + 32;   // 10 warps; two CTAs share an SM
 constexpr uint32_t LBO = 128, SBO = 1024;
 constexpr int A_STAGE_BYTES = BM * BK * 4;   // one of hi / lo
 
@@ -179,7 +179,7 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
-constexpr int RAW_DEPTH = 2;                       // raw A k-stages in flight per producer group
+constexpr int RAW_DEPTH = 3;                       // raw A k-stages in flight per CTA
 constexpr int RAW_ROW_BYTES = BK * 4 + 16;         // 144: row pitch that keeps 16-byte row reads conflict free
 constexpr int RAW_STAGE_BYTES = BM * RAW_ROW_BYTES;
 // Warp-uniform issue: every lane executes the instruction slot, one lane (pred != 0) performs it.  With
@@ -206,14 +206,14 @@ __device__ __forceinline__ void umma_commit_pred(uint32_t pred, uint32_t bar) {
       : "memory");
 }
 
-constexpr int N_GROUPS = 2;                        // producer warpgroups, alternating k-stages
+constexpr int N_GROUPS = 1;                        // producer warpgroups
 constexpr int N_ASLOTS = 2;                        // A stage slots in TMEM (one per producer group)
-constexpr int N_PASS = 3;                          // independent accumulators: lo*hi, hi*lo, hi*hi
+constexpr int N_PASS = 1;                          // accumulators per buffer (independent chains did not help)
 constexpr int MAX_BSLOTS = 8;                      // B stage slots in shared memory (plan.nb <= this)
 constexpr int A_SLOT_COLS = 2 * BK;                // hi | lo
 constexpr int MMA_WARP = 4 * N_GROUPS;
 constexpr int DRAIN_WARP0 = MMA_WARP + 1;
-constexpr int LOADER_WARP = DRAIN_WARP0 + 8;
+constexpr int LOADER_WARP = DRAIN_WARP0 + 4;
 constexpr int RAW_BYTES = N_GROUPS * RAW_DEPTH * RAW_STAGE_BYTES;
 
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
@@ -224,24 +224,25 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
 // Persistent kernel.  CTA c owns n-tile c % n_tiles and m-tiles c / n_tiles, + gridDim.x / n_tiles, ...
 // (gridDim.x is a multiple of n_tiles); all roles run one flat sequence of (m-tile, k-stage) work items
 // g = 0 .. n_items-1, so loads, MMAs and drains of neighbouring tiles overlap.
-// Warps: 0..7  two producer groups (A: global -> cp.async ring -> SE gate, hi/lo split -> TMEM; item g
-//              belongs to group g % 2)
-//        8     MMA issuer (A from TMEM, B from shared memory)
-//        9..16 drain + epilogue (two warps per TMEM lane quadrant, each owning half of the columns)
-//        17    B loader: one bulk copy per k-stage into a ring of `nb` slots, running ahead of the MMAs
+// Two CTAs share an SM (256 TMEM columns, <= 110 KB shared memory, 320 threads each): issuing a tcgen05
+// instruction costs the issuing thread ~75-150 cycles (measured), so a second CTA's MMA warp doubles the rate.
+// Warps: 0..3  producers (A: global -> cp.async ring -> SE gate, hi/lo split -> TMEM)
+//        4     MMA issuer (A from TMEM, B from shared memory)
+//        5..8  drain + epilogue (one warp per TMEM lane quadrant)
+//        9     B loader: one bulk copy per k-stage into a ring of `nb` slots, running ahead of the MMAs
 //              (a bulk copy takes ~1.6k cycles to land); when all nk stages of the n-tile fit in the
 //              ring (`resident`), the weights are loaded once per CTA and stay.
 // TMEM columns: [0, 2*BN_MAX) two accumulators, then N_ASLOTS x 64 columns of A (hi | lo).
 // Wpk: packed weights, n_tiles x nk blocks of [hi: bn x 32 | lo: bn x 32] floats in canonical layout.
 template <int BN_MAX, bool GATE, bool SWISH, bool RESID>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, 2)
 k_pw_gemm_tc(const float* __restrict__ A, const float* __restrict__ Wpk, const float* __restrict__ bias,
              const float* __restrict__ gate, const float* __restrict__ resid, float* __restrict__ C, int M, int N,
              int K, int rows_per_img, int bn, int n_tiles, int nb, int resident) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * N_ASLOTS + 2 * MAX_BSLOTS + 4];
   __shared__ uint32_t s_tmem;
-  constexpr uint32_t TMEM_COLS = 512;
+  constexpr uint32_t TMEM_COLS = 256;               // two CTAs per SM share the 512 columns
   constexpr uint32_t A_COL0 = 2 * N_PASS * BN_MAX;
   static_assert(A_COL0 + N_ASLOTS * A_SLOT_COLS <= TMEM_COLS, "TMEM budget");
   const uint32_t raw_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -369,16 +370,14 @@ k_pw_gemm_tc(const float* __restrict__ A, const float* __restrict__ Wpk, const f
         const uint32_t elected = lane == 0;
         const uint32_t a_hi = tmem_base + A_COL0 + slot * A_SLOT_COLS, a_lo = a_hi + BK;
         const uint32_t b_hi = b_base + bslot * 2 * bsb, b_lo = b_hi + bsb;
-        // The three passes accumulate into three different TMEM accumulators (independent chains),
-        // summed by the drain warps.
         const uint32_t d = tmem_base + b * N_PASS * BN_MAX;
         const int ksteps = min(KSTEPS, (K - s * BK) / UMMA_K);
         for (int j = 0; j < ksteps; ++j) {
           const uint32_t koff = j * 2 * LBO;   // two 16-byte k-chunks of B per MMA; 8 TMEM columns of A
           const uint64_t dbh = make_smem_desc(b_hi + koff), dbl = make_smem_desc(b_lo + koff);
-          umma_tf32_ts_pred(elected, d, a_lo + j * UMMA_K, dbh, idesc, j != 0);
-          umma_tf32_ts_pred(elected, d + BN_MAX, a_hi + j * UMMA_K, dbl, idesc, j != 0);
-          umma_tf32_ts_pred(elected, d + 2 * BN_MAX, a_hi + j * UMMA_K, dbh, idesc, j != 0);
+          umma_tf32_ts_pred(elected, d, a_lo + j * UMMA_K, dbh, idesc, j != 0);   // small terms first
+          umma_tf32_ts_pred(elected, d, a_hi + j * UMMA_K, dbl, idesc, 1);
+          umma_tf32_ts_pred(elected, d, a_hi + j * UMMA_K, dbh, idesc, 1);
         }
         if (lane == 0 && g == 4) trace(6);
         umma_commit_pred(elected, emptyA(slot));
@@ -403,9 +402,9 @@ k_pw_gemm_tc(const float* __restrict__ A, const float* __restrict__ Wpk, const f
     }
   } else {
     // ------------------------------------------------------------------ drain + epilogue
-    constexpr int HALF = BN_MAX / 2;               // columns per drain warp
+    constexpr int HALF = BN_MAX;                   // columns per drain warp (one warp per lane quadrant)
     const int q = warp & 3;                        // TMEM lane quadrant this warp may access
-    const int c_base = ((warp - DRAIN_WARP0) / 4) * HALF;
+    const int c_base = 0;
     const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
     float acc[HALF];
     for (int g = 0; g < n_items; ++g) {
@@ -419,12 +418,10 @@ k_pw_gemm_tc(const float* __restrict__ A, const float* __restrict__ Wpk, const f
 #pragma unroll
       for (int c0 = 0; c0 < HALF; c0 += 16) {
         if (c_base + c0 < bn) {
-          float v0[16], v1[16], v2[16];
-          tmem_ld16(t_row + b * N_PASS * BN_MAX + c_base + c0, v0);
-          tmem_ld16(t_row + (b * N_PASS + 1) * BN_MAX + c_base + c0, v1);
-          tmem_ld16(t_row + (b * N_PASS + 2) * BN_MAX + c_base + c0, v2);
+          float v[16];
+          tmem_ld16(t_row + b * BN_MAX + c_base + c0, v);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) acc[c0 + i] += (v0[i] + v1[i]) + v2[i];
+          for (int i = 0; i < 16; ++i) acc[c0 + i] += v[i];
         }
       }
       tc_fence_before();
@@ -472,7 +469,7 @@ inline Plan make_plan(int N, int K) {
   p.bn_max = 64;
   p.nk = (K + BK - 1) / BK;
   const int slot = 2 * b_stage_bytes(p.bn);
-  p.nb = std::max(2, std::min(MAX_BSLOTS, (224 * 1024 - RAW_BYTES - 1024) / slot));
+  p.nb = std::max(2, std::min(MAX_BSLOTS, (110 * 1024 - RAW_BYTES - 1024) / slot));   // half an SM per CTA
   p.resident = p.nk <= p.nb ? 1 : 0;
   if (p.resident) p.nb = p.nk;
   p.smem_bytes = RAW_BYTES + p.nb * slot + 1024;
