@@ -41,6 +41,14 @@ ALGO_BYTES_PER_FORWARD = 6107136 * 4      # block-bounda
 ALGO_FLOP_PER_FORWARD = 2 * 1456.6e6
 
 
+def workload_config(world):
+    return {'workload': 'configs[1]: 64 synthetic YCB-V crops per GPU (8 frames 640x480 x 8 detections, '
+                        '21 labels), 1 coarse + 4 refine iters, random-init BN-calibrated EfficientNet-B3, '
+                        'pre-rendered views', 'hypotheses_per_gpu': BSZ, 'forwards_per_hypothesis': 5,
+            'l2': 'inputs larger than L2: 295 MB of views + 1.3 GB of activations stream per step',
+            'collective': 'one NCCL all-gather of [64,4,4] poses per step' if world > 1 else 'none'}
+
+
 def measured_peaks():
     p = ROOT / 'MEASURED_PEAKS.json'
     if p.exists():
@@ -116,8 +124,7 @@ def run_reference(args, rank):
     line = dict(metric=METRIC, value=cb['value'], unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=ms * 1e3, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32',
                 data='synthetic', impl='reference',
-                config={'workload': 'configs[1]: 64 synthetic YCB-V crops (8 frames x 8 detections, 21 labels), '
-                                    '1 coarse + 4 refine iters; CPU arm times a 16-hypothesis sample of it'},
+                config=workload_config(args.gpus),
                 cpu_baseline=cb,
                 e2e={'value': cb['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0})
     print(json.dumps(line))
@@ -250,11 +257,7 @@ def main():
             metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
             ms_per_step=ms_total / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
             dtype='f32', data='synthetic',
-            config={'workload': 'configs[1]: 64 synthetic YCB-V crops per GPU (8 frames 640x480 x 8 detections, '
-                                '21 labels), 1 coarse + 4 refine iters, random-init BN-calibrated EfficientNet-B3, '
-                                'pre-rendered views', 'hypotheses_per_gpu': w.n, 'forwards_per_hypothesis': 5,
-                    'l2': 'inputs larger than L2: 295 MB of views + 1.3 GB of activations stream per step',
-                    'collective': 'one NCCL all-gather of [64,4,4] poses per step' if world > 1 else 'none'},
+            config=workload_config(world),
             clocks=clocks,
             e2e={'value': hyps / (ms_e2e * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': int(h2d),
                  'd2h_bytes_per_step': int(d2h), 'ms_per_step': ms_e2e / args.steps},

@@ -557,10 +557,16 @@ int cosyb200_prepare_iter(cosyb200_handle* h, int B, int img_h, int img_w, const
 
 static int launch_crop(cosyb200_handle* h, int B, const float* images, int n_images, int img_h, int img_w,
                        const int32_t* im_ids, const float* boxes_crop, float* crops, cudaStream_t st) {
-  dim3 grid((RENDER_W + CROP_TX - 1) / CROP_TX, (RENDER_H + CROP_TY - 1) / CROP_TY, B), block(CROP_TX, CROP_TY);
+  static bool attr_set = false;
+  const size_t smem = CROP_SMEM_FLOATS * sizeof(float);
+  if (!attr_set) {
+    CB_CUDA(cudaFuncSetAttribute(k_roi_crop, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  dim3 grid(RENDER_H / CROP_PH, B);
   {
     LaunchScope ls(h, CAT_CROP, st);
-    k_roi_crop<<<grid, block, 0, st>>>(B, images, n_images, img_h, img_w, im_ids, boxes_crop, crops);
+    k_roi_crop<<<grid, CROP_THREADS, smem, st>>>(B, images, n_images, img_h, img_w, im_ids, boxes_crop, crops);
   }
   CB_LAUNCH_CHECK();
   return 0;

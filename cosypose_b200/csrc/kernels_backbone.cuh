@@ -3,9 +3,10 @@
 //   k_stem        3x3 s2 6->40 + bias + swish; reads the crop and render planes directly (the
 //                 6-channel concat of pose.py:104 never exists in memory)
 //   k_pw_gemm     1x1 convolution as a row-major GEMM on CUDA cores with fused bias / swish /
-//                 SE gate on the A operand / residual add          (expand, project, head)
-//   k_dwconv      depthwise kxk (k3/k5, s1/s2, static asymmetric "same" padding) + bias + swish,
-//                 also emits deterministic per-tile channel sums for the squeeze step
+//                 SE gate on the A operand / residual add (parity anchor; the product path runs
+//                 kernels_tc.cuh: tcgen05 3xTF32)
+//   k_dwconv_roll depthwise kxk (k3/k5, s1/s2, static asymmetric "same" padding) + bias + swish with
+//                 a register rolling window; emits deterministic per-tile channel sums for the squeeze step
 //   k_se_gate     squeeze-excite: tile sums -> mean -> FC+swish -> FC+sigmoid -> gate[B][Cexp]
 //   k_pool_fc_update  mean pool over 7x10, Linear(1536,9), 6D->R + image-space pose update
 #pragma once
@@ -233,68 +234,8 @@ k_pw_gemm(const float* __restrict__ A, const float* __restrict__ Wkn, const floa
 }
 
 // ------------------------------------------------------------------------------------ depthwise
-// in [B][H][W][C] -> out [B][Ho][Wo][C]; thread = (pixel lane p, channel quad cq) with a fixed
-// channel quad, so the per-tile channel sums reduce without atomics (deterministic).
-//   grid = (tiles_per_img, n_chunks, B); block = Gc * P threads (Gc = C/4/n_chunks channel quads)
+// in [B][H][W][C] -> out [B][Ho][Wo][C]; deterministic per-tile channel sums (no atomics).
 constexpr int DW_MAX_THREADS = 256;
-
-template <int KS, int S>
-__global__ void __launch_bounds__(DW_MAX_THREADS)
-k_dwconv(const float* __restrict__ in, const float* __restrict__ w /*[KS*KS][C]*/,
-         const float* __restrict__ bias, float* __restrict__ out, float* __restrict__ partial,
-         int H, int W, int C, int Ho, int Wo, int pad_lo, int Gc, int P, int pix_per_tile,
-         int tiles_per_img) {
-  __shared__ float4 sred[DW_MAX_THREADS];
-  const int b = blockIdx.z, tile = blockIdx.x;
-  const int tid = threadIdx.x;
-  const int cq = blockIdx.y * Gc + tid % Gc;  // channel quad
-  const int p = tid / Gc;
-  const int c = cq * 4;
-  const int npix = Ho * Wo;
-  const int pix_end = min(npix, (tile + 1) * pix_per_tile);
-  const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + c));
-  const float* inb = in + (size_t)b * H * W * C;
-  float* outb = out + (size_t)b * npix * C;
-  float4 psum = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int pix = tile * pix_per_tile + p; pix < pix_end; pix += P) {
-    const int oy = pix / Wo, ox = pix % Wo;
-    const int iy0 = oy * S - pad_lo, ix0 = ox * S - pad_lo;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int ky = 0; ky < KS; ++ky) {
-      const int iy = iy0 + ky;
-      if (iy < 0 || iy >= H) continue;
-#pragma unroll
-      for (int kx = 0; kx < KS; ++kx) {
-        const int ix = ix0 + kx;
-        if (ix < 0 || ix >= W) continue;
-        float4 v = *reinterpret_cast<const float4*>(inb + ((size_t)iy * W + ix) * C + c);
-        float4 ww = __ldg(reinterpret_cast<const float4*>(w + (size_t)(ky * KS + kx) * C + c));
-        acc.x = fmaf(v.x, ww.x, acc.x);
-        acc.y = fmaf(v.y, ww.y, acc.y);
-        acc.z = fmaf(v.z, ww.z, acc.z);
-        acc.w = fmaf(v.w, ww.w, acc.w);
-      }
-    }
-    float4 o;
-    o.x = swishf(acc.x + bv.x);
-    o.y = swishf(acc.y + bv.y);
-    o.z = swishf(acc.z + bv.z);
-    o.w = swishf(acc.w + bv.w);
-    *reinterpret_cast<float4*>(outb + (size_t)pix * C + c) = o;
-    psum.x += o.x; psum.y += o.y; psum.z += o.z; psum.w += o.w;
-  }
-  sred[tid] = psum;
-  __syncthreads();
-  if (tid < Gc) {
-    float4 s = sred[tid];
-    for (int q = 1; q < P; ++q) {
-      float4 t = sred[q * Gc + tid];
-      s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
-    }
-    *reinterpret_cast<float4*>(partial + ((size_t)b * tiles_per_img + tile) * C + c) = s;
-  }
-}
 
 // Depthwise with a rolling window (stride 1 or 2): a thread owns (channel vector, output column) and
 // walks down TH output rows.  Each input row is loaded once per thread (KS vector loads, horizontally

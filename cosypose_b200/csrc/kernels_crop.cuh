@@ -10,6 +10,12 @@
 // moves a sample across the drop threshold relative to the CPU operator.
 // The image is gathered through im_ids (the reference copies the full frame per hypothesis,
 // integrated/pose_predictor.py:41).  Output: NCHW planes, the layout the stem kernel stages from.
+//
+// The 16-sample sum is separable: out = 1/16 sum_iy vy (hy R[ylo] + ly R[yhi]) with the horizontal
+// pass R[row][pw] = sum_ix vx (hx I[row][xlo] + lx I[row][xhi]).  A CTA owns CROP_PH output rows of
+// one hypothesis, builds R for the few source rows they touch in shared memory (8 loads per entry
+// instead of 64 per output pixel), then combines vertically.  Tiles that would need more than
+// CROP_MAXR source rows (strong zoom-out) take the direct path.
 #pragma once
 #include "common.h"
 
@@ -44,49 +50,109 @@ __device__ __forceinline__ AxisSample make_axis_sample(float start, float bin, i
   return s;
 }
 
-constexpr int CROP_TX = 32, CROP_TY = 8;
+constexpr int CROP_PH = 8;          // output rows per CTA
+constexpr int CROP_MAXR = 16;       // source rows staged per CTA
+constexpr int CROP_THREADS = 320;   // one thread per output column
+constexpr int CROP_SMEM_FLOATS = CROP_MAXR * 3 * RENDER_W;
 
-__global__ void __launch_bounds__(CROP_TX* CROP_TY)
+__global__ void __launch_bounds__(CROP_THREADS)
 k_roi_crop(int B, const float* __restrict__ images, int n_images, int H, int W,
            const int32_t* __restrict__ im_ids, const float* __restrict__ boxes,
            float* __restrict__ crops) {
-  const int b = blockIdx.z;
-  const int pw = blockIdx.x * CROP_TX + threadIdx.x;
-  const int ph = blockIdx.y * CROP_TY + threadIdx.y;
-  if (pw >= RENDER_W || ph >= RENDER_H) return;
+  extern __shared__ float s_R[];   // [rows][3][320]
+  const int b = blockIdx.y;
+  const int ph0 = blockIdx.x * CROP_PH;
+  const int pw = threadIdx.x;
   const float x1 = boxes[b * 4 + 0], y1 = boxes[b * 4 + 1];
   const float x2 = boxes[b * 4 + 2], y2 = boxes[b * 4 + 3];
   const float roi_w = fmaxf(__fsub_rn(x2, x1), 1.0f);
   const float roi_h = fmaxf(__fsub_rn(y2, y1), 1.0f);
   const float bin_w = __fdiv_rn(roi_w, (float)RENDER_W);
   const float bin_h = __fdiv_rn(roi_h, (float)RENDER_H);
-  AxisSample sx[4], sy[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    sx[i] = make_axis_sample(x1, bin_w, pw, i, W);
-    sy[i] = make_axis_sample(y1, bin_h, ph, i, H);
-  }
   const float* img = images + (size_t)im_ids[b] * 3 * H * W;
+
+  AxisSample sx[4];
 #pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    const float* pl = img + (size_t)c * H * W;
-    float acc = 0.f;
+  for (int i = 0; i < 4; ++i) sx[i] = make_axis_sample(x1, bin_w, pw, i, W);
+
+  // source rows touched by the valid y samples of this tile (sample coordinates are monotonic in ph, iy)
+  int r0 = H, r1 = -1;
+  for (int k = 0; k < CROP_PH * 4; ++k) {
+    AxisSample s = make_axis_sample(y1, bin_h, ph0 + k / 4, k % 4, H);
+    if (s.valid) {
+      r0 = min(r0, s.lo);
+      r1 = max(r1, s.hi);
+    }
+  }
+  const int n_rows = r1 - r0 + 1;   // <= 0: every sample of the tile is outside the frame
+  float* out = crops + ((size_t)b * 3 * RENDER_H + ph0) * RENDER_W + pw;
+
+  if (n_rows <= 0) {
 #pragma unroll
-    for (int iy = 0; iy < 4; ++iy) {
-      const float* rlo = pl + (size_t)sy[iy].lo * W;
-      const float* rhi = pl + (size_t)sy[iy].hi * W;
+    for (int c = 0; c < 3; ++c)
+      for (int p = 0; p < CROP_PH; ++p) out[((size_t)c * RENDER_H + p) * RENDER_W] = 0.f;
+    return;
+  }
+  if (n_rows <= CROP_MAXR) {
+    // horizontal pass: thread pw builds R[row][c][pw] for all staged rows
+    for (int r = 0; r < n_rows; ++r) {
 #pragma unroll
-      for (int ix = 0; ix < 4; ++ix) {
-        float w1 = __fmul_rn(sy[iy].h, sx[ix].h), w2 = __fmul_rn(sy[iy].h, sx[ix].l);
-        float w3 = __fmul_rn(sy[iy].l, sx[ix].h), w4 = __fmul_rn(sy[iy].l, sx[ix].l);
-        float v = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w1, __ldg(rlo + sx[ix].lo)),
-                                                __fmul_rn(w2, __ldg(rlo + sx[ix].hi))),
-                                      __fmul_rn(w3, __ldg(rhi + sx[ix].lo))),
-                            __fmul_rn(w4, __ldg(rhi + sx[ix].hi)));
-        if (sy[iy].valid && sx[ix].valid) acc = __fadd_rn(acc, v);
+      for (int c = 0; c < 3; ++c) {
+        const float* row = img + ((size_t)c * H + (r0 + r)) * W;
+        float acc = 0.f;
+#pragma unroll
+        for (int ix = 0; ix < 4; ++ix) {
+          const float v = __fadd_rn(__fmul_rn(sx[ix].h, __ldg(row + sx[ix].lo)), __fmul_rn(sx[ix].l, __ldg(row + sx[ix].hi)));
+          if (sx[ix].valid) acc = __fadd_rn(acc, v);
+        }
+        s_R[(r * 3 + c) * RENDER_W + pw] = acc;
       }
     }
-    crops[(((size_t)b * 3 + c) * RENDER_H + ph) * RENDER_W + pw] = __fdiv_rn(acc, 16.0f);
+    // vertical pass: only this thread's own column of R is read, no barrier needed
+    for (int p = 0; p < CROP_PH; ++p) {
+      float acc[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+      for (int iy = 0; iy < 4; ++iy) {
+        const AxisSample s = make_axis_sample(y1, bin_h, ph0 + p, iy, H);
+        if (s.valid) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const float lo = s_R[((s.lo - r0) * 3 + c) * RENDER_W + pw], hi = s_R[((s.hi - r0) * 3 + c) * RENDER_W + pw];
+            acc[c] = __fadd_rn(acc[c], __fadd_rn(__fmul_rn(s.h, lo), __fmul_rn(s.l, hi)));
+          }
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) out[((size_t)c * RENDER_H + p) * RENDER_W] = __fdiv_rn(acc[c], 16.0f);
+    }
+    return;
+  }
+  // direct path (strong zoom-out): 16 bilinear samples per output pixel
+  for (int p = 0; p < CROP_PH; ++p) {
+    AxisSample sy[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) sy[i] = make_axis_sample(y1, bin_h, ph0 + p, i, H);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float* pl = img + (size_t)c * H * W;
+      float acc = 0.f;
+#pragma unroll
+      for (int iy = 0; iy < 4; ++iy) {
+        const float* rlo = pl + (size_t)sy[iy].lo * W;
+        const float* rhi = pl + (size_t)sy[iy].hi * W;
+#pragma unroll
+        for (int ix = 0; ix < 4; ++ix) {
+          float w1 = __fmul_rn(sy[iy].h, sx[ix].h), w2 = __fmul_rn(sy[iy].h, sx[ix].l);
+          float w3 = __fmul_rn(sy[iy].l, sx[ix].h), w4 = __fmul_rn(sy[iy].l, sx[ix].l);
+          float v = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w1, __ldg(rlo + sx[ix].lo)),
+                                                  __fmul_rn(w2, __ldg(rlo + sx[ix].hi))),
+                                        __fmul_rn(w3, __ldg(rhi + sx[ix].lo))),
+                              __fmul_rn(w4, __ldg(rhi + sx[ix].hi)));
+          if (sy[iy].valid && sx[ix].valid) acc = __fadd_rn(acc, v);
+        }
+      }
+      out[((size_t)c * RENDER_H + p) * RENDER_W] = __fdiv_rn(acc, 16.0f);
+    }
   }
 }
 

@@ -343,7 +343,7 @@ k_pw_gemm_tc(const float* __restrict__ A, const float* __restrict__ Wpk, const f
         lo[c] = tf32_rna(v[c] - h);
         v[c] = h;
       }
-      if (g >= N_ASLOTS) mbar_wait(emptyA(slot), ((g / N_ASLOTS) - 1) & 1);
+      if (g >= N_ASLOTS) mbar_wait(acc_full(slot), ((g / N_ASLOTS) - 1) & 1);   // MMAs of item g-2 done
       tc_fence_after();
       tmem_st32(t_lane + A_COL0 + slot * A_SLOT_COLS, v);
       tmem_st32(t_lane + A_COL0 + slot * A_SLOT_COLS + BK, lo);
@@ -371,18 +371,19 @@ k_pw_gemm_tc(const float* __restrict__ A, const float* __restrict__ Wpk, const f
         const uint32_t a_hi = tmem_base + A_COL0 + slot * A_SLOT_COLS, a_lo = a_hi + BK;
         const uint32_t b_hi = b_base + bslot * 2 * bsb, b_lo = b_hi + bsb;
         const uint32_t d = tmem_base + b * N_PASS * BN_MAX;
-        const int ksteps = min(KSTEPS, (K - s * BK) / UMMA_K);
-        for (int j = 0; j < ksteps; ++j) {
-          const uint32_t koff = j * 2 * LBO;   // two 16-byte k-chunks of B per MMA; 8 TMEM columns of A
-          const uint64_t dbh = make_smem_desc(b_hi + koff), dbl = make_smem_desc(b_lo + koff);
-          umma_tf32_ts_pred(elected, d, a_lo + j * UMMA_K, dbh, idesc, j != 0);   // small terms first
-          umma_tf32_ts_pred(elected, d, a_hi + j * UMMA_K, dbl, idesc, 1);
-          umma_tf32_ts_pred(elected, d, a_hi + j * UMMA_K, dbh, idesc, 1);
+        // Always all 4 k-steps of the stage (operands are zero filled beyond K): a compile-time trip count
+        // lets the descriptors be formed once and stepped by immediates.
+        const uint64_t dbh0 = make_smem_desc(b_hi), dbl0 = make_smem_desc(b_lo);
+#pragma unroll
+        for (int j = 0; j < KSTEPS; ++j) {
+          const uint64_t koff = (uint64_t)((j * 2 * LBO) >> 4);   // two 16-byte k-chunks of B per MMA; 8 TMEM columns of A
+          umma_tf32_ts_pred(elected, d, a_lo + j * UMMA_K, dbh0 + koff, idesc, j != 0);   // small terms first
+          umma_tf32_ts_pred(elected, d, a_hi + j * UMMA_K, dbl0 + koff, idesc, 1);
+          umma_tf32_ts_pred(elected, d, a_hi + j * UMMA_K, dbh0 + koff, idesc, 1);
         }
         if (lane == 0 && g == 4) trace(6);
-        umma_commit_pred(elected, emptyA(slot));
         if (!resident) umma_commit_pred(elected, emptyB(bslot));
-        umma_commit_pred(elected, acc_full(b));
+        umma_commit_pred(elected, acc_full(b));   // also frees A slot g % 2 for the producers
         if (lane == 0 && g < 8) trace(16 + g);
       }
       __syncwarp();
