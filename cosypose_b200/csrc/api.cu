@@ -142,7 +142,7 @@ static int launch_gemm_tc(bool gate, bool swish, bool resid, const float* A, con
 }
 
 // ---- depthwise dispatch ---------------------------------------------------------------------
-struct DwPlan { int n_chunks, Gc, P, tiles; int V, TH, tiles_x; };
+struct DwPlan { int n_chunks, Gc, P, tiles; int V, TH, tiles_x, NX; };
 static DwPlan dw_plan(const BlockSpec& b) {
   // k_dwconv_roll: thread = (channel vector, output column), rolls down TH output rows
   DwPlan p;
@@ -153,7 +153,8 @@ static DwPlan dw_plan(const BlockSpec& b) {
   p.Gc = G / p.n_chunks;
   p.P = DW_MAX_THREADS / p.Gc;
   p.TH = std::min(b.hout, 30);
-  p.tiles_x = (b.wout + p.P - 1) / p.P;
+  p.NX = 4;                                   // adjacent output columns per thread (register blocking)
+  p.tiles_x = (b.wout + p.P * p.NX - 1) / (p.P * p.NX);
   p.tiles = p.tiles_x * ((b.hout + p.TH - 1) / p.TH);
   return p;
 }
@@ -164,10 +165,10 @@ static int launch_dw(const BlockSpec& b, const BlockWeights& w, const float* in,
   dim3 grid(p.tiles, p.n_chunks, B);
   int threads = p.Gc * p.P;
 #define DW_ARGS in, w.dw_w, w.dw_bias, out, partial, b.hin, b.win, b.cexp, b.hout, b.wout, b.pad_lo, p.Gc, p.P, p.TH, p.tiles_x, p.tiles
-  if (b.k == 3 && b.s == 1) k_dwconv_roll<3, 1, 4><<<grid, threads, 0, st>>>(DW_ARGS);
-  else if (b.k == 3 && b.s == 2) k_dwconv_roll<3, 2, 4><<<grid, threads, 0, st>>>(DW_ARGS);
-  else if (b.k == 5 && b.s == 1) k_dwconv_roll<5, 1, 2><<<grid, threads, 0, st>>>(DW_ARGS);
-  else if (b.k == 5 && b.s == 2) k_dwconv_roll<5, 2, 2><<<grid, threads, 0, st>>>(DW_ARGS);
+  if (b.k == 3 && b.s == 1) k_dwconv_roll<3, 1, 4, 4><<<grid, threads, 0, st>>>(DW_ARGS);
+  else if (b.k == 3 && b.s == 2) k_dwconv_roll<3, 2, 4, 4><<<grid, threads, 0, st>>>(DW_ARGS);
+  else if (b.k == 5 && b.s == 1) k_dwconv_roll<5, 1, 2, 4><<<grid, threads, 0, st>>>(DW_ARGS);
+  else if (b.k == 5 && b.s == 2) k_dwconv_roll<5, 2, 2, 4><<<grid, threads, 0, st>>>(DW_ARGS);
   else { set_error("unsupported depthwise k=%d s=%d", b.k, b.s); return COSYB200_EINVAL; }
 #undef DW_ARGS
   CB_LAUNCH_CHECK();

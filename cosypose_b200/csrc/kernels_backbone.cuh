@@ -15,8 +15,11 @@
 
 namespace cosyb {
 
-__device__ __forceinline__ float swishf(float v) { return __fdividef(v, 1.0f + expf(-v)); }
-__device__ __forceinline__ float sigmoidf_(float v) { return __fdividef(1.0f, 1.0f + expf(-v)); }
+// x * sigmoid(x) with the hardware exp2 / reciprocal approximations (5 instructions: FMUL, MUFU.EX2, FADD,
+// MUFU.RCP, FMUL; ~2 ulp).  The accurate expf costs ~15 instructions per element and made the epilogue of
+// the expand convolutions the slowest stage of the pipeline (measured with the in-kernel cycle trace).
+__device__ __forceinline__ float swishf(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
+__device__ __forceinline__ float sigmoidf_(float v) { return __fdividef(1.0f, 1.0f + __expf(-v)); }
 
 // ------------------------------------------------------------------------------------------ stem
 constexpr int STEM_TX = 32, STEM_TY = 8;                    // output tile
@@ -253,7 +256,7 @@ template <int V> __device__ __forceinline__ void vzero(float* a) {
   for (int i = 0; i < V; ++i) a[i] = 0.f;
 }
 
-template <int KS, int S, int V>
+template <int KS, int S, int V, int NX>
 __global__ void __launch_bounds__(DW_MAX_THREADS)
 k_dwconv_roll(const float* __restrict__ in, const float* __restrict__ w /*[KS*KS][C]*/,
               const float* __restrict__ bias, float* __restrict__ out, float* __restrict__ partial,
@@ -262,14 +265,15 @@ k_dwconv_roll(const float* __restrict__ in, const float* __restrict__ w /*[KS*KS
   using VT = typename VecT<V>::T;
   constexpr int NSLOT = (KS + S - 1) / S;      // output rows in flight per thread
   constexpr int PERIOD = S * NSLOT;            // the (input row -> slot, tap row) pattern repeats with this period
+  constexpr int NIN = (NX - 1) * S + KS;       // input columns feeding the thread's NX adjacent outputs
   __shared__ float sred[DW_MAX_THREADS * V];
   const int b = blockIdx.z, tile = blockIdx.x;
   const int tile_x = tile % tiles_x, tile_y = tile / tiles_x;
   const int tid = threadIdx.x;
   const int c = (blockIdx.y * Gc + tid % Gc) * V;
-  const int ox = tile_x * PX + tid / Gc;
+  const int ox0 = (tile_x * PX + tid / Gc) * NX;
   const int oy0 = tile_y * TH;
-  const bool col_ok = ox < Wo;
+  const bool col_ok = ox0 < Wo;
   const float* inb = in + (size_t)b * H * W * C + c;
   float* outb = out + (size_t)b * Ho * Wo * C + c;
 
@@ -288,25 +292,27 @@ k_dwconv_roll(const float* __restrict__ in, const float* __restrict__ w /*[KS*KS
 #pragma unroll
     for (int i = 0; i < V; ++i) bv[i] = tp[i];
   }
-  float acc[NSLOT][V];
+  float acc[NSLOT][NX][V];
 #pragma unroll
-  for (int s = 0; s < NSLOT; ++s) vzero<V>(acc[s]);
+  for (int s = 0; s < NSLOT; ++s)
+#pragma unroll
+    for (int x = 0; x < NX; ++x) vzero<V>(acc[s][x]);
   float psum[V];
   vzero<V>(psum);
 
   // input rows r = 0 .. (TH-1)*S + KS - 1 relative to iy0 = oy0*S - pad; input row r feeds output row
   // (r - ky) / S with tap row ky whenever that division is exact.
   const int n_in_rows = (TH - 1) * S + KS;
-  const int iy0 = oy0 * S - pad, ix0 = ox * S - pad;
+  const int iy0 = oy0 * S - pad, ix0 = ox0 * S - pad;
   for (int r0 = 0; r0 < n_in_rows; r0 += PERIOD) {
 #pragma unroll
     for (int j = 0; j < PERIOD; ++j) {
       const int r = r0 + j;
       const int iy = iy0 + r;
       if (r < n_in_rows && iy >= 0 && iy < H && col_ok) {
-        float v[KS][V];
+        float v[NIN][V];
 #pragma unroll
-        for (int kx = 0; kx < KS; ++kx) {
+        for (int kx = 0; kx < NIN; ++kx) {
           const int ix = ix0 + kx;
           if (ix >= 0 && ix < W) {
             VT t = *reinterpret_cast<const VT*>(inb + ((size_t)iy * W + ix) * C);
@@ -322,9 +328,12 @@ k_dwconv_roll(const float* __restrict__ in, const float* __restrict__ w /*[KS*KS
           if ((j - ky + PERIOD * KS) % S == 0) {
             const int slot = ((j - ky + PERIOD * KS) / S) % NSLOT;
 #pragma unroll
-            for (int kx = 0; kx < KS; ++kx)
+            for (int x = 0; x < NX; ++x)
 #pragma unroll
-              for (int i = 0; i < V; ++i) acc[slot][i] = fmaf(v[kx][i], wreg[ky * KS + kx][i], acc[slot][i]);
+              for (int kx = 0; kx < KS; ++kx)
+#pragma unroll
+                for (int i = 0; i < V; ++i)
+                  acc[slot][x][i] = fmaf(v[x * S + kx][i], wreg[ky * KS + kx][i], acc[slot][x][i]);
           }
         }
       }
@@ -334,15 +343,21 @@ k_dwconv_roll(const float* __restrict__ in, const float* __restrict__ w /*[KS*KS
         const int num = r - (KS - 1);
         const int oyr = num >= 0 ? num / S : -1;
         if (oyr >= 0 && oyr < TH && oy0 + oyr < Ho && col_ok) {
-          float o[V];
 #pragma unroll
-          for (int i = 0; i < V; ++i) {
-            o[i] = swishf(acc[slot_done][i] + bv[i]);
-            psum[i] += o[i];
+          for (int x = 0; x < NX; ++x) {
+            if (ox0 + x < Wo) {
+              float o[V];
+#pragma unroll
+              for (int i = 0; i < V; ++i) {
+                o[i] = swishf(acc[slot_done][x][i] + bv[i]);
+                psum[i] += o[i];
+              }
+              *reinterpret_cast<VT*>(outb + ((size_t)(oy0 + oyr) * Wo + ox0 + x) * C) = pack_vec(o);
+            }
           }
-          *reinterpret_cast<VT*>(outb + ((size_t)(oy0 + oyr) * Wo + ox) * C) = pack_vec(o);
         }
-        vzero<V>(acc[slot_done]);
+#pragma unroll
+        for (int x = 0; x < NX; ++x) vzero<V>(acc[slot_done][x]);
       }
     }
   }

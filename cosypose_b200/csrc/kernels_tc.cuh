@@ -68,6 +68,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "WAIT_LOOP:\n"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
       "@p bra WAIT_DONE;\n"
+      "nanosleep.u32 40;\n"
       "bra WAIT_LOOP;\n"
       "WAIT_DONE:\n"
       "}\n" ::"r"(bar), "r"(parity)
@@ -135,10 +136,11 @@ __device__ __forceinline__ uint32_t make_idesc(int bn) {
   return d;
 }
 
+// Round to the nearest TF32 (ties away from zero) with integer ALU ops, bit-identical to cvt.rna.tf32.f32
+// for finite inputs and to the host-side packing.  cvt runs on the 16-lane conversion pipe, which the
+// producers (2 conversions per A element) and the swish epilogue (MUFU.EX2 + MUFU.RCP) were saturating.
 __device__ __forceinline__ float tf32_rna(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
 }
 
 // Optional cycle trace of CTA 0 for tuning (cosyb200_debug_trace): slot -> clock64() stamp.
@@ -179,7 +181,7 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
-constexpr int RAW_DEPTH = 3;                       // raw A k-stages in flight per CTA
+constexpr int RAW_DEPTH = 2;                       // raw A k-stages in flight per CTA (two CTAs per SM)
 constexpr int RAW_ROW_BYTES = BK * 4 + 16;         // 144: row pitch that keeps 16-byte row reads conflict free
 constexpr int RAW_STAGE_BYTES = BM * RAW_ROW_BYTES;
 // Warp-uniform issue: every lane executes the instruction slot, one lane (pred != 0) performs it.  With
@@ -215,6 +217,8 @@ constexpr int MMA_WARP = 4 * N_GROUPS;
 constexpr int DRAIN_WARP0 = MMA_WARP + 1;
 constexpr int LOADER_WARP = DRAIN_WARP0 + 4;
 constexpr int RAW_BYTES = N_GROUPS * RAW_DEPTH * RAW_STAGE_BYTES;
+constexpr int STG_PITCH = 68;                      // floats per staged output row (64 + 4: conflict-free 16-byte accesses)
+constexpr int STG_BYTES = 4 * 32 * STG_PITCH * 4;  // one 32-row staging tile per drain warp
 
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
@@ -242,11 +246,13 @@ k_pw_gemm_tc(const float* __restrict__ A, const float* __restrict__ Wpk, const f
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * N_ASLOTS + 2 * MAX_BSLOTS + 4];
   __shared__ uint32_t s_tmem;
+  __shared__ __align__(16) float s_bias[64];          // bias of this CTA's n-tile (fixed for the CTA's lifetime)
   constexpr uint32_t TMEM_COLS = 256;               // two CTAs per SM share the 512 columns
   constexpr uint32_t A_COL0 = 2 * N_PASS * BN_MAX;
   static_assert(A_COL0 + N_ASLOTS * A_SLOT_COLS <= TMEM_COLS, "TMEM budget");
   const uint32_t raw_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t b_base = raw_base + RAW_BYTES;     // B stage slots
+  float* stg_base = reinterpret_cast<float*>(smem_raw + (raw_base - smem_u32(smem_raw)) + RAW_BYTES + nb * 2 * b_stage_bytes(bn));
   const int tid = threadIdx.x, lane = tid % 32;
   const int warp = __shfl_sync(0xffffffffu, tid / 32, 0);   // tells the compiler the role branches are warp-uniform
   const int nk = (K + BK - 1) / BK;
@@ -277,6 +283,10 @@ k_pw_gemm_tc(const float* __restrict__ A, const float* __restrict__ Wpk, const f
       mbar_init(acc_empty(b), DRAIN_THREADS);
     }
     fence_barrier_init();
+  }
+  if (tid < 64) {
+    const int n = (blockIdx.x % n_tiles) * bn + tid;
+    s_bias[tid] = (tid < bn && n < N) ? __ldg(bias + n) : 0.f;
   }
   if (warp == MMA_WARP) tmem_alloc(smem_u32(&s_tmem), TMEM_COLS);
   tc_fence_before();
@@ -427,18 +437,35 @@ k_pw_gemm_tc(const float* __restrict__ A, const float* __restrict__ Wpk, const f
       }
       tc_fence_before();
       mbar_arrive(acc_empty(b));
-      if (tid == DRAIN_WARP0 * 32 && g < 6) trace(24 + g);
+      if (tid == DRAIN_WARP0 * 32 && g < 4) trace(24 + g);
       if (s == nk - 1) {
-        const int m = (m_first + (g / nk) * m_step) * BM + q * 32 + lane;
+        // Epilogue.  A thread owns one output row; storing it directly would make every warp store touch 32
+        // different 128-byte lines (measured: ~8.5k cycles per tile, the slowest stage of the expand layers).
+        // The warp's 32 x bn tile is staged through shared memory and written out row-contiguously.
+        const int m_base = (m_first + (g / nk) * m_step) * BM + q * 32;
         const int n_base = n_tile * bn;
-        if (m < M) {
+        float* stg = stg_base + (warp - DRAIN_WARP0) * (32 * STG_PITCH);
+        if (tid == DRAIN_WARP0 * 32 && g / nk == 1) trace(28);
+        // branch-free: columns >= bn hold zeros (zero weights, zero bias) and are never copied out
 #pragma unroll
-          for (int c0 = 0; c0 < HALF; c0 += 4) {
-            const int c = c_base + c0, n = n_base + c;
-            if (c < bn && n < N) {
-              const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + n));
-              float4 o = make_float4(acc[c0] + bv.x, acc[c0 + 1] + bv.y, acc[c0 + 2] + bv.z, acc[c0 + 3] + bv.w);
-              if (SWISH) { o.x = swishf(o.x); o.y = swishf(o.y); o.z = swishf(o.z); o.w = swishf(o.w); }
+        for (int c0 = 0; c0 < HALF; c0 += 4) {
+          const float4 bv = *reinterpret_cast<const float4*>(s_bias + c0);
+          float4 o = make_float4(acc[c0] + bv.x, acc[c0 + 1] + bv.y, acc[c0 + 2] + bv.z, acc[c0 + 3] + bv.w);
+          if (SWISH) { o.x = swishf(o.x); o.y = swishf(o.y); o.z = swishf(o.z); o.w = swishf(o.w); }
+          *reinterpret_cast<float4*>(stg + lane * STG_PITCH + c0) = o;
+        }
+        __syncwarp();
+        if (tid == DRAIN_WARP0 * 32 && g / nk == 1) trace(29);
+        // copy out: lpr lanes per row (power of two >= bn/4), 32/lpr rows per pass, no divisions
+        const int qn = bn >> 2;                   // float4 per staged row
+        const int lpr_log = qn <= 4 ? 2 : (qn <= 8 ? 3 : 4);
+        const int c4 = lane & ((1 << lpr_log) - 1), r_lane = lane >> lpr_log, r_step = 32 >> lpr_log;
+        const int n = n_base + c4 * 4;
+        if (c4 < qn && n < N) {
+          for (int r = r_lane; r < 32; r += r_step) {
+            const int m = m_base + r;
+            if (m < M) {
+              float4 o = *reinterpret_cast<const float4*>(stg + r * STG_PITCH + c4 * 4);
               if (RESID) {
                 const float4 rr = *reinterpret_cast<const float4*>(resid + (size_t)m * N + n);
                 o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
@@ -447,6 +474,8 @@ k_pw_gemm_tc(const float* __restrict__ A, const float* __restrict__ Wpk, const f
             }
           }
         }
+        __syncwarp();
+        if (tid == DRAIN_WARP0 * 32 && g / nk == 1) trace(30);
       }
     }
   }
@@ -470,10 +499,10 @@ inline Plan make_plan(int N, int K) {
   p.bn_max = 64;
   p.nk = (K + BK - 1) / BK;
   const int slot = 2 * b_stage_bytes(p.bn);
-  p.nb = std::max(2, std::min(MAX_BSLOTS, (110 * 1024 - RAW_BYTES - 1024) / slot));   // half an SM per CTA
+  p.nb = std::max(2, std::min(MAX_BSLOTS, (110 * 1024 - RAW_BYTES - STG_BYTES - 1024) / slot));   // half an SM per CTA
   p.resident = p.nk <= p.nb ? 1 : 0;
   if (p.resident) p.nb = p.nk;
-  p.smem_bytes = RAW_BYTES + p.nb * slot + 1024;
+  p.smem_bytes = RAW_BYTES + p.nb * slot + STG_BYTES + 1024;
   return p;
 }
 
