@@ -41,6 +41,7 @@ _SIGS = {
     'cosyb200_debug_trace': ([_P, _P], c_int),
     'cosyb200_profile_enable': ([_P, c_int], c_int),
     'cosyb200_profile_read': ([_P, c_int, _P, _P], c_int),
+    'cosyb200_profile_read_blocks': ([_P, c_int, _P], c_int),
     'cosyb200_ransac_infos': ([c_int, _P, _P, c_int, c_int, POINTER(c_int64), POINTER(c_int64), _P, _P], c_int),
     'cosyb200_ransac_models': ([_P, c_int64, _P, _P, _P, _P, _P], c_int),
     'cosyb200_ransac_score': ([_P, c_int64, _P, _P, _P, _P, _P, _P], c_int),

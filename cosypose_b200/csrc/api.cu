@@ -12,6 +12,7 @@
 #include "kernels_ransac.cuh"
 #include "kernels_ba.cuh"
 #include "kernels_tc.cuh"
+#include "kernels_dwtile.cuh"
 
 namespace cosyb {
 
@@ -44,8 +45,10 @@ int prof_resolve(cosyb200_handle* h) {
     float ms = 0.f;
     CB_CUDA(cudaEventElapsedTime(&ms, h->ev_pool[2 * i], h->ev_pool[2 * i + 1]));
     h->cat_ms[h->ev_cat[i]] += ms;
+    h->blk_ms[h->ev_cat[i]][h->ev_blk[i]] += ms;
   }
   h->ev_cat.clear();
+  h->ev_blk.clear();
   return 0;
 }
 
@@ -101,13 +104,14 @@ static void launch_gemm(bool gate, bool swish, bool resid, const float* A, const
 }
 
 // tensor-core path: Wpk = tc::pack_weights image of the [N][K] weight
-template <int BN_MAX, bool G, bool S, bool R>
-static int launch_gemm_tc_inst(const tc::Plan& p, const float* A, const float* Wpk, const float* bias, const float* g,
+static int g_tc_groups = 0;   // 0: pick per layer, 1 / 2: force the producer-group variant (set_option "tc_groups")
+template <int BN_MAX, bool G, bool S, bool R, int NG>
+static int launch_gemm_tc_inst(const float* A, const float* Wpk, const float* bias, const float* g,
                                const float* r, float* C, int M, int N, int K, int rows_per_img, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    CB_CUDA(cudaFuncSetAttribute(tc::k_pw_gemm_tc<BN_MAX, G, S, R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 112 * 1024));
+    CB_CUDA(cudaFuncSetAttribute(tc::k_pw_gemm_tc<BN_MAX, G, S, R, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 NG == 1 ? 112 * 1024 : 202 * 1024));
     attr_set = true;
   }
   static int n_sms = 0;
@@ -116,11 +120,12 @@ static int launch_gemm_tc_inst(const tc::Plan& p, const float* A, const float* W
     CB_CUDA(cudaGetDevice(&dev));
     CB_CUDA(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
   }
+  const tc::Plan p = tc::make_plan(N, K, NG);
   const int m_tiles = (M + tc::BM - 1) / tc::BM;
-  const int grid = std::min(m_tiles, std::max(1, 2 * n_sms / p.n_tiles)) * p.n_tiles;   // multiple of n_tiles, 2 CTAs / SM
-  tc::k_pw_gemm_tc<BN_MAX, G, S, R><<<grid, tc::THREADS, p.smem_bytes, st>>>(A, Wpk, bias, g, r, C, M, N, K,
-                                                                             rows_per_img, p.bn, p.n_tiles, p.nb,
-                                                                             p.resident);
+  const int slots = NG == 1 ? 2 * n_sms : n_sms;
+  const int grid = std::min(m_tiles, std::max(1, slots / p.n_tiles)) * p.n_tiles;   // multiple of n_tiles
+  tc::k_pw_gemm_tc<BN_MAX, G, S, R, NG><<<grid, tc::threads_for(NG), p.smem_bytes, st>>>(
+      A, Wpk, bias, g, r, C, M, N, K, rows_per_img, p.bn, p.n_tiles, p.nb, p.resident);
   CB_LAUNCH_CHECK();
   return 0;
 }
@@ -128,9 +133,12 @@ static int launch_gemm_tc_inst(const tc::Plan& p, const float* A, const float* W
 static int launch_gemm_tc(bool gate, bool swish, bool resid, const float* A, const float* Wpk, const float* bias,
                           const float* g, const float* r, float* C, int M, int N, int K, int rows_per_img,
                           cudaStream_t st) {
-  const tc::Plan p = tc::make_plan(N, K);
-#define TC_ARGS p, A, Wpk, bias, g, r, C, M, N, K, rows_per_img, st
-#define TC_DISPATCH(G, S, R) launch_gemm_tc_inst<64, G, S, R>(TC_ARGS)
+  const tc::Plan p1 = tc::make_plan(N, K, 1);
+  const int tiles = ((M + tc::BM - 1) / tc::BM) * p1.n_tiles;
+  // fewer tiles than two-per-SM CTA slots: one bigger CTA per SM with two producer groups
+  const int ng = g_tc_groups ? g_tc_groups : (tiles <= 296 ? 2 : 1);
+#define TC_ARGS A, Wpk, bias, g, r, C, M, N, K, rows_per_img, st
+#define TC_DISPATCH(G, S, R) (ng == 2 ? launch_gemm_tc_inst<64, G, S, R, 2>(TC_ARGS) : launch_gemm_tc_inst<64, G, S, R, 1>(TC_ARGS))
   if (!gate && swish && !resid) return TC_DISPATCH(false, true, false);
   if (gate && !swish && !resid) return TC_DISPATCH(true, false, false);
   if (gate && !swish && resid) return TC_DISPATCH(true, false, true);
@@ -175,6 +183,37 @@ static int launch_dw(const BlockSpec& b, const BlockWeights& w, const float* in,
   return 0;
 }
 
+// smem-tiled depthwise + fused squeeze-excite (kernels_dwtile.cuh); writes h->gate itself
+template <int KS, int S, int WO>
+static int launch_dw_tile_inst(const DwTilePlan& p, const BlockSpec& b, const BlockWeights& w, const float* in, float* out,
+                               cosyb200_handle* h, int B, cudaStream_t st) {
+  static int smem_set = 0;
+  if (p.smem_bytes > smem_set) {
+    CB_CUDA(cudaFuncSetAttribute(k_dw_tile<KS, S, WO>, cudaFuncAttributeMaxDynamicSharedMemorySize, p.smem_bytes));
+    smem_set = p.smem_bytes;
+  }
+  dim3 grid(p.n_chunks, p.n_strips, B);
+  k_dw_tile<KS, S, WO><<<grid, DWT_THREADS, p.smem_bytes, st>>>(
+      in, w.dw_w, w.dw_bias, out, h->pool_partial, b.hin, b.win, b.cexp, b.hout, b.pad_lo, p.R, b.cse, w.se_r_w);
+  CB_LAUNCH_CHECK();
+  return 0;
+}
+
+static int launch_dw_tile(const DwTilePlan& p, const BlockSpec& b, const BlockWeights& w, const float* in, float* out,
+                          cosyb200_handle* h, int B, cudaStream_t st) {
+#define DWT(KS, S, WO) if (b.k == KS && b.s == S && b.wout == WO) return launch_dw_tile_inst<KS, S, WO>(p, b, w, in, out, h, B, st)
+  DWT(5, 1, 40); DWT(3, 2, 20); DWT(3, 1, 20); DWT(5, 1, 20); DWT(5, 2, 10); DWT(5, 1, 10); DWT(3, 1, 10);
+#undef DWT
+  set_error("launch_dw_tile: no instance for k=%d s=%d wout=%d", b.k, b.s, b.wout);
+  return COSYB200_EINVAL;
+}
+
+static bool use_dw_tile(const cosyb200_handle* h, const BlockSpec& b) {
+  if (h->dw_impl == 0) return false;
+  const DwTilePlan p = dw_tile_plan(b);
+  return p.ok && (b.wout == 40 || b.wout == 20 || b.wout == 10) && !(b.k == 3 && b.wout == 40);
+}
+
 // ---- trunk forward --------------------------------------------------------------------------
 static int net_forward(cosyb200_handle* h, int slot, int B, const float* crops, const void* renders,
                        int render_u8, float* pose9, float* const* taps, const float* TCO_in, const float* K_crop,
@@ -197,6 +236,7 @@ static int net_forward(cosyb200_handle* h, int slot, int B, const float* crops, 
   for (size_t i = 0; i < h->blocks.size(); ++i) {
     const BlockSpec& b = h->blocks[i];
     const BlockWeights& w = m.blocks[i];
+    h->cur_block = (int)i;
     const float* x = h->act[cur];
     float* y = h->act[cur ^ 1];
     const int Min = B * b.hin * b.win, Mout = B * b.hout * b.wout;
@@ -212,13 +252,21 @@ static int net_forward(cosyb200_handle* h, int slot, int B, const float* crops, 
       CB_LAUNCH_CHECK();
       dw_in = h->buf_e;
     }
+    const bool tile_dw = use_dw_tile(h, b);
     {
       LaunchScope ls(h, CAT_DW, st);
-      rc = launch_dw(b, w, dw_in, h->buf_d, h->pool_partial, B, st);
+      if (tile_dw) rc = launch_dw_tile(dw_tile_plan(b), b, w, dw_in, h->buf_d, h, B, st);
+      else rc = launch_dw(b, w, dw_in, h->buf_d, h->pool_partial, B, st);
     }
     if (rc) return rc;
     DwPlan p = dw_plan(b);
-    {
+    if (tile_dw) {
+      const DwTilePlan tp = dw_tile_plan(b);
+      LaunchScope ls(h, CAT_SE, st);
+      const dim3 g2((b.cexp + SE2_THREADS - 1) / SE2_THREADS, B);
+      k_se_fc2<<<g2, SE2_THREADS, 0, st>>>(h->pool_partial, tp.n_strips * tp.n_chunks, b.cexp, b.cse,
+                                           1.0f / float(b.hout * b.wout), w.se_r_b, w.se_e_w, w.se_e_b, h->gate);
+    } else {
       LaunchScope ls(h, CAT_SE, st);
       static bool se_attr = false;
       if (!se_attr) {
@@ -246,6 +294,7 @@ static int net_forward(cosyb200_handle* h, int slot, int B, const float* crops, 
     rc = tap(1 + (int)i, y, (size_t)Mout * b.cout);
     if (rc) return rc;
   }
+  h->cur_block = cosyb200_handle::N_BLK - 1;
   const BlockSpec& last = h->blocks.back();
   const int n_pos = last.hout * last.wout;
   {
@@ -314,6 +363,7 @@ int cosyb200_create(cosyb200_handle** out, int device, int max_batch) {
     if (b.e != 1) e = std::max(e, (size_t)b.hin * b.win * b.cexp);
     d = std::max(d, (size_t)b.hout * b.wout * b.cexp);
     part = std::max(part, (size_t)dw_plan(b).tiles * b.cexp);
+    if (dw_tile_plan(b).ok) part = std::max(part, (size_t)dw_tile_plan(b).n_strips * dw_tile_plan(b).n_chunks * b.cse);
     cmax = std::max(cmax, (size_t)b.cexp);
   }
   e = std::max(e, (size_t)h->blocks.back().hout * h->blocks.back().wout * N_FEATURES);
@@ -643,6 +693,16 @@ int cosyb200_set_option(cosyb200_handle* h, const char* name, int value) {
     h->gemm_impl = value;
     return COSYB200_OK;
   }
+  if (strcmp(name, "tc_groups") == 0) {
+    CB_CHECK_ARG(value >= 0 && value <= 2, "set_option: tc_groups must be 0 (per layer), 1 or 2");
+    g_tc_groups = value;
+    return COSYB200_OK;
+  }
+  if (strcmp(name, "dw_impl") == 0) {
+    CB_CHECK_ARG(value == 0 || value == 1, "set_option: dw_impl must be 0 (rolling window + separate SE) or 1 (tiled + split SE)");
+    h->dw_impl = value;
+    return COSYB200_OK;
+  }
   set_error("set_option: unknown option %s", name);
   return COSYB200_EINVAL;
 }
@@ -708,6 +768,18 @@ int cosyb200_profile_read(cosyb200_handle* h, int reset, int64_t* launches10, do
     if (ms10) ms10[i] = h->cat_ms[i];
     if (reset) { h->launches[i] = 0; h->cat_ms[i] = 0; }
   }
+  return COSYB200_OK;
+}
+
+int cosyb200_profile_read_blocks(cosyb200_handle* h, int reset, double* ms /*[10][32]*/) {
+  CB_CHECK_ARG(h != nullptr && ms != nullptr, "profile_read_blocks: bad arguments");
+  DeviceGuard guard(h->device);
+  if (int rc = prof_resolve(h)) return rc;
+  for (int c = 0; c < cosyb200_handle::N_CAT; ++c)
+    for (int b = 0; b < cosyb200_handle::N_BLK; ++b) {
+      ms[c * cosyb200_handle::N_BLK + b] = h->blk_ms[c][b];
+      if (reset) h->blk_ms[c][b] = 0;
+    }
   return COSYB200_OK;
 }
 

@@ -106,7 +106,12 @@ struct cosyb200_handle {
   static constexpr int N_CAT = 10;
   int64_t launches[N_CAT] = {0};
   double cat_ms[N_CAT] = {0};
+  static constexpr int N_BLK = 32;     // per-MBConv-block split of cat_ms (index 31: outside the blocks)
+  double blk_ms[N_CAT][N_BLK] = {{0}};
+  int cur_block = N_BLK - 1;
+  std::vector<int> ev_blk;
   bool profiling = false;
+  int dw_impl = 1;     // depthwise of the small-spatial blocks: 0 = rolling window + k_se_gate, 1 = k_dw_tile + k_se_fc2
   int gemm_impl = 1;   // 1x1 convolutions: 0 = CUDA-core fp32 kernel, 1 = tcgen05 3xTF32 kernel
   std::vector<cudaEvent_t> ev_pool;   // pairs: [2*i] start, [2*i+1] stop
   std::vector<int> ev_cat;            // category of each recorded pair
@@ -132,6 +137,7 @@ struct LaunchScope {
     h->ev_stream = st;
     cudaEventRecord(h->ev_pool[h->ev_cat.size() * 2], st);
     h->ev_cat.push_back(cat);
+    h->ev_blk.push_back(h->cur_block);
     rec = true;
   }
   ~LaunchScope() {

@@ -40,6 +40,7 @@ constexpr int KSTEPS = BK / UMMA_K;
 constexpr int PRODUCER_THREADS = 128;
 constexpr int DRAIN_THREADS = 128;
 constexpr int THREADS = PRODUCER_THREADS + 32 + DRAIN_THREADS + 32;   // 10 warps; two CTAs share an SM
+__host__ __device__ constexpr int threads_for(int ng) { return ng * PRODUCER_THREADS + 32 + DRAIN_THREADS + 32; }
 constexpr uint32_t LBO = 128, SBO = 1024;
 constexpr int A_STAGE_BYTES = BM * BK * 4;   // one of hi / lo
 
@@ -208,15 +209,11 @@ __device__ __forceinline__ void umma_commit_pred(uint32_t pred, uint32_t bar) {
       : "memory");
 }
 
-constexpr int N_GROUPS = 1;                        // producer warpgroups
 constexpr int N_ASLOTS = 2;                        // A stage slots in TMEM (one per producer group)
 constexpr int N_PASS = 1;                          // accumulators per buffer (independent chains did not help)
 constexpr int MAX_BSLOTS = 8;                      // B stage slots in shared memory (plan.nb <= this)
 constexpr int A_SLOT_COLS = 2 * BK;                // hi | lo
-constexpr int MMA_WARP = 4 * N_GROUPS;
-constexpr int DRAIN_WARP0 = MMA_WARP + 1;
-constexpr int LOADER_WARP = DRAIN_WARP0 + 4;
-constexpr int RAW_BYTES = N_GROUPS * RAW_DEPTH * RAW_STAGE_BYTES;
+__host__ __device__ constexpr int raw_bytes(int ng) { return ng * RAW_DEPTH * RAW_STAGE_BYTES; }
 constexpr int STG_PITCH = 68;                      // floats per staged output row (64 + 4: conflict-free 16-byte accesses)
 constexpr int STG_BYTES = 4 * 32 * STG_PITCH * 4;  // one 32-row staging tile per drain warp
 
@@ -238,11 +235,18 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
 //              ring (`resident`), the weights are loaded once per CTA and stay.
 // TMEM columns: [0, 2*BN_MAX) two accumulators, then N_ASLOTS x 64 columns of A (hi | lo).
 // Wpk: packed weights, n_tiles x nk blocks of [hi: bn x 32 | lo: bn x 32] floats in canonical layout.
-template <int BN_MAX, bool GATE, bool SWISH, bool RESID>
-__global__ void __launch_bounds__(THREADS, 2)
+// NG = producer warpgroups: 1 -> 10 warps, two CTAs per SM; 2 -> 14 warps, one CTA per SM, the two groups fill
+// alternate k-stages (for layers with fewer tiles than CTA slots, where a second CTA per SM would sit empty).
+template <int BN_MAX, bool GATE, bool SWISH, bool RESID, int NG>
+__global__ void __launch_bounds__(threads_for(NG), NG == 1 ? 2 : 1)
 k_pw_gemm_tc(const float* __restrict__ A, const float* __restrict__ Wpk, const float* __restrict__ bias,
              const float* __restrict__ gate, const float* __restrict__ resid, float* __restrict__ C, int M, int N,
              int K, int rows_per_img, int bn, int n_tiles, int nb, int resident) {
+  constexpr int N_GROUPS = NG;
+  constexpr int MMA_WARP = 4 * N_GROUPS;
+  constexpr int DRAIN_WARP0 = MMA_WARP + 1;
+  constexpr int LOADER_WARP = DRAIN_WARP0 + 4;
+  constexpr int RAW_BYTES = raw_bytes(NG);
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * N_ASLOTS + 2 * MAX_BSLOTS + 4];
   __shared__ uint32_t s_tmem;
@@ -327,9 +331,14 @@ k_pw_gemm_tc(const float* __restrict__ A, const float* __restrict__ Wpk, const f
       const int g = grp + i * N_GROUPS;
       const int m = (m_first + (g / nk) * m_step) * BM + row, k0 = (g % nk) * BK;
       const int slot = g % N_ASLOTS;
+      const bool tr = tg == 0 && g == 6;
+      if (tr) trace(8);
       cp_async_wait<RAW_DEPTH - 2>();               // this thread's copies of item i have landed
+      if (tr) trace(9);
       named_bar_sync(1 + grp, PRODUCER_THREADS);    // ... and everybody else's; slot (i-1) is free again
+      if (tr) trace(10);
       issue_raw(i + RAW_DEPTH - 1);
+      if (tr) trace(11);
       const uint32_t src = ring + (i % RAW_DEPTH) * RAW_STAGE_BYTES + row * RAW_ROW_BYTES;
       float v[BK];
 #pragma unroll
@@ -353,14 +362,17 @@ k_pw_gemm_tc(const float* __restrict__ A, const float* __restrict__ Wpk, const f
         lo[c] = tf32_rna(v[c] - h);
         v[c] = h;
       }
+      if (tr) trace(12);
       if (g >= N_ASLOTS) mbar_wait(acc_full(slot), ((g / N_ASLOTS) - 1) & 1);   // MMAs of item g-2 done
       tc_fence_after();
+      if (tr) trace(13);
       tmem_st32(t_lane + A_COL0 + slot * A_SLOT_COLS, v);
       tmem_st32(t_lane + A_COL0 + slot * A_SLOT_COLS + BK, lo);
       tmem_st_wait();
       tc_fence_before();
+      if (tr) trace(14);
       mbar_arrive(fullA(slot));
-      if (tg == 0 && g < 8) trace(8 + g);
+      if (tr) trace(15);
     }
     cp_async_wait<0>();
   } else if (warp == MMA_WARP) {
@@ -369,13 +381,13 @@ k_pw_gemm_tc(const float* __restrict__ A, const float* __restrict__ Wpk, const f
     for (int g = 0; g < n_items; ++g) {
       const int s = g % nk, slot = g % N_ASLOTS, b = g & 1;
       const int bslot = resident ? s : g % nb;
-      if (lane == 0 && g == 4) trace(4);
+      if (lane == 0 && g == 6) trace(4);
       if (g >= 2) mbar_wait(acc_empty(b), ((g >> 1) - 1) & 1);
       if (!resident) mbar_wait(fullB(bslot), (g / nb) & 1);
       else if (g < nk) mbar_wait(fullB(bslot), 0);
       mbar_wait(fullA(slot), (g / N_ASLOTS) & 1);
       tc_fence_after();
-      if (lane == 0 && g == 4) trace(5);
+      if (lane == 0 && g == 6) trace(5);
       {
         const uint32_t elected = lane == 0;
         const uint32_t a_hi = tmem_base + A_COL0 + slot * A_SLOT_COLS, a_lo = a_hi + BK;
@@ -391,7 +403,7 @@ k_pw_gemm_tc(const float* __restrict__ A, const float* __restrict__ Wpk, const f
           umma_tf32_ts_pred(elected, d, a_hi + j * UMMA_K, dbl0 + koff, idesc, 1);
           umma_tf32_ts_pred(elected, d, a_hi + j * UMMA_K, dbh0 + koff, idesc, 1);
         }
-        if (lane == 0 && g == 4) trace(6);
+        if (lane == 0 && g == 6) trace(6);
         if (!resident) umma_commit_pred(elected, emptyB(bslot));
         umma_commit_pred(elected, acc_full(b));   // also frees A slot g % 2 for the producers
         if (lane == 0 && g < 8) trace(16 + g);
@@ -424,8 +436,11 @@ k_pw_gemm_tc(const float* __restrict__ A, const float* __restrict__ Wpk, const f
 #pragma unroll
         for (int i = 0; i < HALF; ++i) acc[i] = 0.f;
       }
+      const bool trd = tid == DRAIN_WARP0 * 32 && g == 6;
+      if (trd) trace(24);
       mbar_wait(acc_full(b), (g >> 1) & 1);
       tc_fence_after();
+      if (trd) trace(25);
 #pragma unroll
       for (int c0 = 0; c0 < HALF; c0 += 16) {
         if (c_base + c0 < bn) {
@@ -436,8 +451,9 @@ k_pw_gemm_tc(const float* __restrict__ A, const float* __restrict__ Wpk, const f
         }
       }
       tc_fence_before();
+      if (trd) trace(26);
       mbar_arrive(acc_empty(b));
-      if (tid == DRAIN_WARP0 * 32 && g < 4) trace(24 + g);
+      if (trd) trace(27);
       if (s == nk - 1) {
         // Epilogue.  A thread owns one output row; storing it directly would make every warp store touch 32
         // different 128-byte lines (measured: ~8.5k cycles per tile, the slowest stage of the expand layers).
@@ -492,14 +508,16 @@ k_pw_gemm_tc(const float* __restrict__ A, const float* __restrict__ Wpk, const f
 // ---- host side: tile plan and weight packing -------------------------------------------------------
 struct Plan { int bn, bn_max, n_tiles, nk, nb, resident, smem_bytes; };
 
-inline Plan make_plan(int N, int K) {
+inline Plan make_plan(int N, int K, int ng = 1) {
+  const int RAW_BYTES = raw_bytes(ng);
+  const int budget = ng == 1 ? 110 * 1024 : 200 * 1024;   // half an SM per CTA, or the whole SM
   Plan p;
   p.n_tiles = (N + 63) / 64;
   p.bn = (((N + p.n_tiles - 1) / p.n_tiles) + 15) / 16 * 16;
   p.bn_max = 64;
   p.nk = (K + BK - 1) / BK;
   const int slot = 2 * b_stage_bytes(p.bn);
-  p.nb = std::max(2, std::min(MAX_BSLOTS, (110 * 1024 - RAW_BYTES - STG_BYTES - 1024) / slot));   // half an SM per CTA
+  p.nb = std::max(2, std::min(MAX_BSLOTS, (budget - RAW_BYTES - STG_BYTES - 1024) / slot));
   p.resident = p.nk <= p.nb ? 1 : 0;
   if (p.resident) p.nb = p.nk;
   p.smem_bytes = RAW_BYTES + p.nb * slot + STG_BYTES + 1024;

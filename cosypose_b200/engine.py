@@ -241,6 +241,12 @@ class Engine:
         _lib.check(self._L.cosyb200_profile_read(self._h, int(reset), _np_ptr(n), _np_ptr(ms)), 'profile_read')
         return {c: (int(n[i]), float(ms[i])) for i, c in enumerate(self.CATEGORIES)}
 
+    def profile_read_blocks(self, reset=True):
+        """{category: [device_ms per MBConv block (index 31: outside the blocks)]} while profiling."""
+        ms = np.zeros((10, 32), dtype=np.float64)
+        _lib.check(self._L.cosyb200_profile_read_blocks(self._h, int(reset), _np_ptr(ms)), 'profile_read_blocks')
+        return {c: ms[i].tolist() for i, c in enumerate(self.CATEGORIES)}
+
     # -- multiview ----------------------------------------------------------------------------
     def ransac_models(self, poses, cand_label_ids, seeds):
         n_seeds = seeds.shape[1]

@@ -154,6 +154,8 @@ int cosyb200_debug_trace(cosyb200_handle* h, long long* trace_dev);
  * device time accumulated per category (adds launch overhead: use outside timed regions). */
 int cosyb200_profile_enable(cosyb200_handle* h, int on);
 int cosyb200_profile_read(cosyb200_handle* h, int reset, int64_t* launches10, double* ms10);
+/* The same device time split per MBConv block: ms[category * 32 + block], block 31 = stem / head / outside. */
+int cosyb200_profile_read_blocks(cosyb200_handle* h, int reset, double* ms320);
 
 /* ---- multiview candidate matching (reference: multiview/ransac.py:137-199) ---- */
 

@@ -36,9 +36,11 @@ def _ref(A, W, bias, gate, rows, resid, swish):
     return y
 
 
-@pytest.mark.parametrize('impl', [1, 0])
-def test_all_trunk_shapes(eng, impl):
+@pytest.mark.parametrize('impl,groups', [(1, 1), (1, 2), (0, 0)])
+def test_all_trunk_shapes(eng, impl, groups):
+    """groups: producer-warpgroup variant of the tensor-core kernel (1: two CTAs per SM, 2: one CTA per SM)."""
     dev = eng.device
+    eng.set_option('tc_groups', groups)
     gen = torch.Generator().manual_seed(0)
     worst = 0.0
     for K, N, kind in _trunk_shapes():
@@ -56,12 +58,15 @@ def test_all_trunk_shapes(eng, impl):
         err = (out.cpu().double() - ref).abs().max().item() / ref.abs().max().item()
         worst = max(worst, err)
         assert err < 2e-6, (K, N, kind, err)
+    eng.set_option('tc_groups', 0)
     print('worst relative error', worst)
 
 
+@pytest.mark.parametrize('groups', [1, 2])
 @pytest.mark.parametrize('M', [1, 127, 128, 129, 4480, 19200 * 2 + 5])
-def test_row_counts(eng, M):
+def test_row_counts(eng, M, groups):
     dev = eng.device
+    eng.set_option('tc_groups', groups)
     gen = torch.Generator().manual_seed(M)
     K, N = 48, 288
     A = torch.randn((M, K), generator=gen)
@@ -69,4 +74,5 @@ def test_row_counts(eng, M):
     bias = torch.randn(N, generator=gen)
     out = eng.debug_pointwise(1, A.to(dev), W, bias, swish=True)
     ref = _ref(A, W, bias, None, 1, None, True)
+    eng.set_option('tc_groups', 0)
     assert (out.cpu().double() - ref).abs().max().item() < 2e-6 * ref.abs().max().item()
