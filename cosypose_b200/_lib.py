@@ -8,7 +8,9 @@ import ctypes
 from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
 from pathlib import Path
 
-LIB_PATH = Path(__file__).resolve().parent / 'libcosyb200.so'
+import os
+
+LIB_PATH = Path(os.environ.get('COSYB200_LIB') or Path(__file__).resolve().parent / 'libcosyb200.so')
 
 EINVAL, ECUDA, ESTATE, ENOMEM = -1, -2, -3, -4
 SLOT_COARSE, SLOT_REFINER = 0, 1
@@ -39,6 +41,7 @@ _SIGS = {
     'cosyb200_set_option': ([_P, c_char_p, c_int], c_int),
     'cosyb200_debug_pointwise': ([_P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, c_int, _P, c_int, _P, _P], c_int),
     'cosyb200_debug_trace': ([_P, _P], c_int),
+    'cosyb200_debug_dump': ([_P, c_int, _P, _P, _P], c_int),
     'cosyb200_profile_enable': ([_P, c_int], c_int),
     'cosyb200_profile_read': ([_P, c_int, _P, _P], c_int),
     'cosyb200_profile_read_blocks': ([_P, c_int, _P], c_int),

@@ -104,6 +104,7 @@ static void launch_gemm(bool gate, bool swish, bool resid, const float* A, const
 }
 
 // tensor-core path: Wpk = tc::pack_weights image of the [N][K] weight
+static int g_tc_dbg = 0;
 static int g_tc_groups = 0;   // 0: pick per layer, 1 / 2: force the producer-group variant (set_option "tc_groups")
 template <int BN_MAX, bool G, bool S, bool R, int NG>
 static int launch_gemm_tc_inst(const float* A, const float* Wpk, const float* bias, const float* g,
@@ -124,8 +125,15 @@ static int launch_gemm_tc_inst(const float* A, const float* Wpk, const float* bi
   const int m_tiles = (M + tc::BM - 1) / tc::BM;
   const int slots = NG == 1 ? 2 * n_sms : n_sms;
   const int grid = std::min(m_tiles, std::max(1, slots / p.n_tiles)) * p.n_tiles;   // multiple of n_tiles
+  if (g_tc_dbg & 4) cudaStreamSynchronize(st);
+  CUtensorMap tmA;
+  if (!tc::make_a_tensor_map(&tmA, A, M, K)) {
+    set_error("launch_gemm_tc: cuTensorMapEncodeTiled failed (A=%p M=%d K=%d)", (const void*)A, M, K);
+    return COSYB200_ECUDA;
+  }
   tc::k_pw_gemm_tc<BN_MAX, G, S, R, NG><<<grid, tc::threads_for(NG), p.smem_bytes, st>>>(
-      A, Wpk, bias, g, r, C, M, N, K, rows_per_img, p.bn, p.n_tiles, p.nb, p.resident);
+      tmA, A, Wpk, bias, g, r, C, M, N, K, rows_per_img, p.bn, p.n_tiles, p.nb, p.resident);
+  if (g_tc_dbg & 8) cudaStreamSynchronize(st);
   CB_LAUNCH_CHECK();
   return 0;
 }
@@ -251,6 +259,8 @@ static int net_forward(cosyb200_handle* h, int slot, int B, const float* crops, 
                   b.cexp, b.cin, 1, st);
       CB_LAUNCH_CHECK();
       dw_in = h->buf_e;
+      if ((int)i == h->dump_block && h->dump_e)
+        CB_CUDA(cudaMemcpyAsync(h->dump_e, h->buf_e, (size_t)Min * b.cexp * 4, cudaMemcpyDeviceToDevice, st));
     }
     const bool tile_dw = use_dw_tile(h, b);
     {
@@ -280,6 +290,10 @@ static int net_forward(cosyb200_handle* h, int slot, int B, const float* crops, 
                                                       w.se_e_b, h->gate);
     }
     CB_LAUNCH_CHECK();
+    if ((int)i == h->dump_block) {
+      if (h->dump_d) CB_CUDA(cudaMemcpyAsync(h->dump_d, h->buf_d, (size_t)Mout * b.cexp * 4, cudaMemcpyDeviceToDevice, st));
+      if (h->dump_gate) CB_CUDA(cudaMemcpyAsync(h->dump_gate, h->gate, (size_t)B * b.cexp * 4, cudaMemcpyDeviceToDevice, st));
+    }
     {
       LaunchScope ls(h, CAT_PROJECT, st);
       if (h->gemm_impl == 1) {
@@ -693,6 +707,10 @@ int cosyb200_set_option(cosyb200_handle* h, const char* name, int value) {
     h->gemm_impl = value;
     return COSYB200_OK;
   }
+  if (strcmp(name, "tc_dbg") == 0) {
+    g_tc_dbg = value;
+    return COSYB200_OK;
+  }
   if (strcmp(name, "tc_groups") == 0) {
     CB_CHECK_ARG(value >= 0 && value <= 2, "set_option: tc_groups must be 0 (per layer), 1 or 2");
     g_tc_groups = value;
@@ -740,6 +758,13 @@ int cosyb200_debug_pointwise(cosyb200_handle* h, int impl, int M, int N, int K, 
   if (rc) return rc;
   if (e != cudaSuccess) { set_error("debug_pointwise: %s", cudaGetErrorString(e)); return COSYB200_ECUDA; }
   CB_LAUNCH_CHECK();
+  return COSYB200_OK;
+}
+
+int cosyb200_debug_dump(cosyb200_handle* h, int block, float* expanded, float* dw_out, float* gate) {
+  CB_CHECK_ARG(h != nullptr, "debug_dump: null handle");
+  h->dump_block = block;
+  h->dump_e = expanded; h->dump_d = dw_out; h->dump_gate = gate;
   return COSYB200_OK;
 }
 

@@ -112,6 +112,9 @@ struct cosyb200_handle {
   std::vector<int> ev_blk;
   bool profiling = false;
   int dw_impl = 1;     // depthwise of the small-spatial blocks: 0 = rolling window + k_se_gate, 1 = k_dw_tile + k_se_fc2
+  // debugging aid (cosyb200_debug_dump): copies of block `dump_block`'s internal tensors
+  int dump_block = -1;
+  float* dump_e = nullptr; float* dump_d = nullptr; float* dump_gate = nullptr;
   int gemm_impl = 1;   // 1x1 convolutions: 0 = CUDA-core fp32 kernel, 1 = tcgen05 3xTF32 kernel
   std::vector<cudaEvent_t> ev_pool;   // pairs: [2*i] start, [2*i+1] stop
   std::vector<int> ev_cat;            // category of each recorded pair

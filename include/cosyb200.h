@@ -145,6 +145,10 @@ int cosyb200_debug_pointwise(cosyb200_handle* h, int impl, int M, int N, int K, 
 /* Tuning aid: when trace_dev (32 int64 slots, device memory) is non-NULL, CTA (0,0) of the tensor-core
  * 1x1 kernel stores clock64() stamps of its pipeline events there; NULL switches it off. */
 int cosyb200_debug_trace(cosyb200_handle* h, long long* trace_dev);
+/* Debugging aid: during the following trunk forwards, copy MBConv block `block`'s expanded activation
+   [B*Hin*Win][Cexp], depthwise output [B*Hout*Wout][Cexp] and squeeze-excite gate [B][Cexp] into the given
+   device buffers (NULL = skip; block -1 = off). */
+int cosyb200_debug_dump(cosyb200_handle* h, int block, float* expanded, float* dw_out, float* gate);
 
 /* Launch accounting (no reference counterpart; the reference times with a wall-clock Timer,
  * utils/timer.py:4-36).  Every kernel the engine launches is counted per category:

@@ -248,6 +248,29 @@ def test_batch_invariance_and_determinism(dev):
     assert (res[0][sub] - ref).abs().max() < TOL_POSE
 
 
+def test_trunk_repeats_bit_identically(dev):
+    """Eight trunk forwards at the benchmark batch: every block-boundary activation is bit-identical.  (The
+    tensor-core kernels hand tiles between warps through mbarriers thousands of times per launch; a missing
+    dependency or a split warp shows up here as a few differing rows, not in a tolerance test.)"""
+    from cosypose_b200.engine import Engine
+    B = 64
+    gen = torch.Generator().manual_seed(3)
+    crops = torch.rand((B, 3, 240, 320), generator=gen).to(dev)
+    renders = torch.rand((B, 3, 240, 320), generator=gen).to(dev)
+    for groups in (1, 0):
+        eng = Engine(0, max_batch=B)
+        eng.load_pose_model(0, state_dict(0))
+        eng.set_option('tc_groups', groups)
+        _, t0 = eng.net_forward(0, crops, renders, taps=True)
+        t0 = {k: v.clone() for k, v in t0.items()}
+        for _ in range(7):
+            _, t1 = eng.net_forward(0, crops, renders, taps=True)
+            for name in t0:
+                assert torch.equal(t0[name], t1[name]), (groups, name)
+        eng.set_option('tc_groups', 0)
+        eng.close()
+
+
 def test_errors(engine, small, dev):
     with pytest.raises(AssertionError):
         engine.net_forward(0, torch.zeros((9, 3, 240, 320), device=dev), torch.zeros((9, 3, 240, 320), device=dev))
