@@ -41,6 +41,29 @@ ALGO_BYTES_PER_FORWARD = 6107136 * 4      # block-bounda
 ALGO_FLOP_PER_FORWARD = 2 * 1456.6e6
 
 
+def kernel_algorithmic_bytes():
+    """Bytes each kernel category must move per forward in the one-kernel-per-stage design (its input read once,
+    its output written once, fp32; weights are L2-resident): the per-kernel roofline numerators.  The whole-trunk
+    figure of SURVEY.md section 8(d), ALGO_BYTES_PER_FORWARD, counts only the block-boundary activations."""
+    from cosypose_b200 import effnet_spec as spec
+    shapes = spec.activation_shapes()
+    out = dict(stem=(shapes[0][1] * shapes[0][2] * 6 + shapes[1][1] * shapes[1][2] * shapes[1][3]) * 4,
+               expand_1x1=0, depthwise=0, project_1x1=0)
+    for b, (_, hi, wi, _), (_, ho, wo, _) in zip(spec.BLOCKS, shapes[1:-2], shapes[2:-1]):
+        if b.e != 1:
+            out['expand_1x1'] += hi * wi * (b.cin + b.cexp) * 4
+        out['depthwise'] += (hi * wi + ho * wo) * b.cexp * 4
+        out['project_1x1'] += ho * wo * (b.cexp + b.cout * (2 if b.skip else 1)) * 4
+    _, h, w, c = shapes[-2]
+    out['head_1x1'] = h * w * (c + spec.N_FEATURES) * 4
+    return out
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures
+# (profiles/README.md), keyed by kernel category; None where no capture exists
+NCU_TRAFFIC_NOTE = 'profiles/README.md'
+
+
 def workload_config(world):
     return {'workload': 'configs[1]: 64 synthetic YCB-V crops per GPU (8 frames 640x480 x 8 detections, '
                         '21 labels), 1 coarse + 4 refine iters, random-init BN-calibrated EfficientNet-B3, '
@@ -253,6 +276,10 @@ def main():
         bb_ms = sum(prof[c][1] for c in backbone_cats) / prof_steps          # per step, this rank
         achieved = fwd_per_step * ALGO_BYTES_PER_FORWARD / (bb_ms * 1e-3) / 1e9 if bb_ms > 0 else None
         tot_prof = sum(ms for _, ms in prof.values())
+        kbytes = kernel_algorithmic_bytes()
+        by_kernel_gbs = {c: round(fwd_per_step * kbytes[c] / (prof[c][1] / prof_steps * 1e-3) / 1e9, 1)
+                         for c in kbytes if prof[c][1] > 0}
+        dominant = max(kbytes, key=lambda c: prof[c][1])
         line = dict(
             metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
             ms_per_step=ms_total / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
@@ -268,6 +295,13 @@ def main():
                       'algorithmic_bytes_per_launch': fwd_per_step * ALGO_BYTES_PER_FORWARD,
                       'launch_ms': bb_ms,
                       'tflops': fwd_per_step * ALGO_FLOP_PER_FORWARD / (bb_ms * 1e-3) / 1e12 if bb_ms > 0 else None,
+                      'dominant_kernel': {'category': dominant, 'achieved': by_kernel_gbs[dominant],
+                                          'frac': round(by_kernel_gbs[dominant] / peak, 4), 'unit': 'GB/s',
+                                          'algorithmic_bytes_per_step': int(fwd_per_step * kbytes[dominant]),
+                                          'launches_per_step': int(prof[dominant][0] / prof_steps),
+                                          'traffic': NCU_TRAFFIC_NOTE},
+                      'by_kernel_gbs': by_kernel_gbs,
+                      'by_kernel_frac': {c: round(v / peak, 4) for c, v in by_kernel_gbs.items()},
                       'by_kernel_ms_per_step': {c: round(ms / prof_steps, 4) for c, (_, ms) in prof.items() if ms > 0},
                       'by_kernel_share': {c: round(ms / tot_prof, 4) for c, (_, ms) in prof.items() if ms > 0}},
         )

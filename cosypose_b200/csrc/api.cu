@@ -104,7 +104,6 @@ static void launch_gemm(bool gate, bool swish, bool resid, const float* A, const
 }
 
 // tensor-core path: Wpk = tc::pack_weights image of the [N][K] weight
-static int g_tc_dbg = 0;
 static int g_tc_groups = 0;   // 0: pick per layer, 1 / 2: force the producer-group variant (set_option "tc_groups")
 template <int BN_MAX, bool G, bool S, bool R, int NG>
 static int launch_gemm_tc_inst(const float* A, const float* Wpk, const float* bias, const float* g,
@@ -125,15 +124,8 @@ static int launch_gemm_tc_inst(const float* A, const float* Wpk, const float* bi
   const int m_tiles = (M + tc::BM - 1) / tc::BM;
   const int slots = NG == 1 ? 2 * n_sms : n_sms;
   const int grid = std::min(m_tiles, std::max(1, slots / p.n_tiles)) * p.n_tiles;   // multiple of n_tiles
-  if (g_tc_dbg & 4) cudaStreamSynchronize(st);
-  CUtensorMap tmA;
-  if (!tc::make_a_tensor_map(&tmA, A, M, K)) {
-    set_error("launch_gemm_tc: cuTensorMapEncodeTiled failed (A=%p M=%d K=%d)", (const void*)A, M, K);
-    return COSYB200_ECUDA;
-  }
   tc::k_pw_gemm_tc<BN_MAX, G, S, R, NG><<<grid, tc::threads_for(NG), p.smem_bytes, st>>>(
-      tmA, A, Wpk, bias, g, r, C, M, N, K, rows_per_img, p.bn, p.n_tiles, p.nb, p.resident);
-  if (g_tc_dbg & 8) cudaStreamSynchronize(st);
+      A, Wpk, bias, g, r, C, M, N, K, rows_per_img, p.bn, p.n_tiles, p.nb, p.resident);
   CB_LAUNCH_CHECK();
   return 0;
 }
@@ -191,35 +183,36 @@ static int launch_dw(const BlockSpec& b, const BlockWeights& w, const float* in,
   return 0;
 }
 
-// smem-tiled depthwise + fused squeeze-excite (kernels_dwtile.cuh); writes h->gate itself
-template <int KS, int S, int WO>
+// smem-tiled depthwise (kernels_dwtile.cuh); the squeeze-excite gate is finished by k_se_fc2
+template <int KS, int S, int WO, int XU>
 static int launch_dw_tile_inst(const DwTilePlan& p, const BlockSpec& b, const BlockWeights& w, const float* in, float* out,
                                cosyb200_handle* h, int B, cudaStream_t st) {
   static int smem_set = 0;
   if (p.smem_bytes > smem_set) {
-    CB_CUDA(cudaFuncSetAttribute(k_dw_tile<KS, S, WO>, cudaFuncAttributeMaxDynamicSharedMemorySize, p.smem_bytes));
+    CB_CUDA(cudaFuncSetAttribute(k_dw_tile<KS, S, WO, XU>, cudaFuncAttributeMaxDynamicSharedMemorySize, p.smem_bytes));
     smem_set = p.smem_bytes;
   }
-  dim3 grid(p.n_chunks, p.n_strips, B);
-  k_dw_tile<KS, S, WO><<<grid, DWT_THREADS, p.smem_bytes, st>>>(
-      in, w.dw_w, w.dw_bias, out, h->pool_partial, b.hin, b.win, b.cexp, b.hout, b.pad_lo, p.R, b.cse, w.se_r_w);
+  dim3 grid(p.n_chunks, p.n_strips * p.n_xt, B);
+  k_dw_tile<KS, S, WO, XU><<<grid, DWT_THREADS, p.smem_bytes, st>>>(
+      in, w.dw_w, w.dw_bias, out, h->pool_partial, b.hin, b.win, b.cexp, b.hout, b.wout, b.pad_lo, p.R, p.n_xt, b.cse,
+      w.se_r_w);
   CB_LAUNCH_CHECK();
   return 0;
 }
 
 static int launch_dw_tile(const DwTilePlan& p, const BlockSpec& b, const BlockWeights& w, const float* in, float* out,
                           cosyb200_handle* h, int B, cudaStream_t st) {
-#define DWT(KS, S, WO) if (b.k == KS && b.s == S && b.wout == WO) return launch_dw_tile_inst<KS, S, WO>(p, b, w, in, out, h, B, st)
-  DWT(5, 1, 40); DWT(3, 2, 20); DWT(3, 1, 20); DWT(5, 1, 20); DWT(5, 2, 10); DWT(5, 1, 10); DWT(3, 1, 10);
+#define DWT(KS, S, WO, XU) \
+  if (b.k == KS && b.s == S && p.wo == WO && p.xu == XU) return launch_dw_tile_inst<KS, S, WO, XU>(p, b, w, in, out, h, B, st)
+  DWT(5, 1, 40, 1); DWT(3, 2, 20, 1); DWT(3, 1, 20, 1); DWT(5, 1, 20, 1);
+  DWT(5, 2, 10, 1); DWT(5, 1, 10, 1); DWT(3, 1, 10, 1);
 #undef DWT
   set_error("launch_dw_tile: no instance for k=%d s=%d wout=%d", b.k, b.s, b.wout);
   return COSYB200_EINVAL;
 }
 
 static bool use_dw_tile(const cosyb200_handle* h, const BlockSpec& b) {
-  if (h->dw_impl == 0) return false;
-  const DwTilePlan p = dw_tile_plan(b);
-  return p.ok && (b.wout == 40 || b.wout == 20 || b.wout == 10) && !(b.k == 3 && b.wout == 40);
+  return h->dw_impl != 0 && dw_tile_plan(b).ok;
 }
 
 // ---- trunk forward --------------------------------------------------------------------------
@@ -274,7 +267,7 @@ static int net_forward(cosyb200_handle* h, int slot, int B, const float* crops, 
       const DwTilePlan tp = dw_tile_plan(b);
       LaunchScope ls(h, CAT_SE, st);
       const dim3 g2((b.cexp + SE2_THREADS - 1) / SE2_THREADS, B);
-      k_se_fc2<<<g2, SE2_THREADS, 0, st>>>(h->pool_partial, tp.n_strips * tp.n_chunks, b.cexp, b.cse,
+      k_se_fc2<<<g2, SE2_THREADS, 0, st>>>(h->pool_partial, tp.n_strips * tp.n_xt * tp.n_chunks, b.cexp, b.cse,
                                            1.0f / float(b.hout * b.wout), w.se_r_b, w.se_e_w, w.se_e_b, h->gate);
     } else {
       LaunchScope ls(h, CAT_SE, st);
@@ -377,7 +370,8 @@ int cosyb200_create(cosyb200_handle** out, int device, int max_batch) {
     if (b.e != 1) e = std::max(e, (size_t)b.hin * b.win * b.cexp);
     d = std::max(d, (size_t)b.hout * b.wout * b.cexp);
     part = std::max(part, (size_t)dw_plan(b).tiles * b.cexp);
-    if (dw_tile_plan(b).ok) part = std::max(part, (size_t)dw_tile_plan(b).n_strips * dw_tile_plan(b).n_chunks * b.cse);
+    if (dw_tile_plan(b).ok)
+      part = std::max(part, (size_t)dw_tile_plan(b).n_strips * dw_tile_plan(b).n_xt * dw_tile_plan(b).n_chunks * b.cse);
     cmax = std::max(cmax, (size_t)b.cexp);
   }
   e = std::max(e, (size_t)h->blocks.back().hout * h->blocks.back().wout * N_FEATURES);
@@ -705,10 +699,6 @@ int cosyb200_set_option(cosyb200_handle* h, const char* name, int value) {
   if (strcmp(name, "gemm_impl") == 0) {
     CB_CHECK_ARG(value == 0 || value == 1, "set_option: gemm_impl must be 0 (cuda cores) or 1 (tcgen05)");
     h->gemm_impl = value;
-    return COSYB200_OK;
-  }
-  if (strcmp(name, "tc_dbg") == 0) {
-    g_tc_dbg = value;
     return COSYB200_OK;
   }
   if (strcmp(name, "tc_groups") == 0) {

@@ -3,7 +3,7 @@
 //
 // k_dwconv_roll walks an image column by column with one thread per (channel vector, 4 columns); at 15x20
 // and 7x10 that leaves ~14 warps per SM, each one a serial chain of row loads, and the launch runs 5-10x
-// below both the HBM and the FMA bound.  Here a CTA owns (image, 32 channels, strip of output rows):
+// below both the HBM and the FMA bound.  Here a CTA owns (image, 32 channels, tile of output rows x columns):
 //   1. the zero-padded input strip [rows][cols][32 channels] is staged in shared memory with 16-byte loads
 //      (a pixel's 32 channels are one 128-byte line of the NHWC activation);
 //   2. lane = channel, warp = output row: every input value is read once from shared memory (stride-32
@@ -25,20 +25,22 @@ constexpr int DWT_THREADS = 256;
 constexpr int DWT_WARPS = DWT_THREADS / 32;
 constexpr int DWT_CC = 32;   // channels per CTA
 
-// grid = (ceil(C / 32), n_strips, B); dynamic smem = ((R-1)*S + KS) * ((WO-1)*S + KS) * 32 floats
-template <int KS, int S, int WO>
+// A CTA's output tile is R rows x (WO * XU) columns; a warp works on units of (row, WO adjacent columns).
+// grid = (ceil(C / 32), n_strips * n_xtiles, B); dynamic smem = ((R-1)*S + KS) * ((WO*XU-1)*S + KS) * 32 floats
+template <int KS, int S, int WO, int XU>
 __global__ void __launch_bounds__(DWT_THREADS)
 k_dw_tile(const float* __restrict__ in, const float* __restrict__ w /*[KS*KS][C]*/, const float* __restrict__ bias,
-          float* __restrict__ out, float* __restrict__ partial_r /*[B][n_strips][n_chunks][Cse]*/, int H, int W,
-          int C, int Ho, int pad, int R, int Cse, const float* __restrict__ wr /*[Cse][C]*/) {
-  constexpr int WP = (WO - 1) * S + KS;
+          float* __restrict__ out, float* __restrict__ partial_r /*[B][n_strips * n_xtiles][n_chunks][Cse]*/, int H,
+          int W, int C, int Ho, int Wo, int pad, int R, int n_xt, int Cse, const float* __restrict__ wr /*[Cse][C]*/) {
+  constexpr int WP = (WO * XU - 1) * S + KS;   // staged columns
+  constexpr int UP = (WO - 1) * S + KS;        // columns read by one unit
   extern __shared__ __align__(16) float s_tile[];
   __shared__ float s_red[DWT_WARPS][DWT_CC];
   __shared__ __align__(16) float s_csum[DWT_CC];
-  const int strip = blockIdx.y, b = blockIdx.z, n_strips = gridDim.y;
+  const int strip = blockIdx.y / n_xt, xt = blockIdx.y % n_xt, b = blockIdx.z, n_strips = gridDim.y;
   const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
   const int c0 = blockIdx.x * DWT_CC;
-  const int oy0 = strip * R;
+  const int oy0 = strip * R, ox0 = xt * WO * XU;
   const int rows = min(R, Ho - oy0);
   const int HP = (rows - 1) * S + KS;
   const int iy0 = oy0 * S - pad;
@@ -50,7 +52,7 @@ k_dw_tile(const float* __restrict__ in, const float* __restrict__ w /*[KS*KS][C]
   for (int i = tid; i < n_v4; i += DWT_THREADS) {
     const int pix = i >> 3, q = i & 7;
     const int py = pix / WP, px = pix - py * WP;
-    const int iy = iy0 + py, ix = px - pad;
+    const int iy = iy0 + py, ix = ox0 * S + px - pad;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (iy >= 0 && iy < H && ix >= 0 && ix < W && c0 + 4 * q < C)
       v = __ldg(reinterpret_cast<const float4*>(inb + ((size_t)iy * W + ix) * C + 4 * q));
@@ -64,17 +66,18 @@ k_dw_tile(const float* __restrict__ in, const float* __restrict__ w /*[KS*KS][C]
   const float bv = cok ? __ldg(bias + c) : 0.f;
   __syncthreads();
 
-  // ---- depthwise: warp = output row, lane = channel
+  // ---- depthwise: warp = (output row, column group), lane = channel
   float psum = 0.f;
-  for (int r = wp; r < rows; r += DWT_WARPS) {
+  for (int u = wp; u < rows * XU; u += DWT_WARPS) {
+    const int r = u / XU, xu = u % XU;
     float acc[WO];
 #pragma unroll
     for (int x = 0; x < WO; ++x) acc[x] = 0.f;
 #pragma unroll
     for (int ky = 0; ky < KS; ++ky) {
-      const float* srow = s_tile + (size_t)((r * S + ky) * WP) * DWT_CC + lane;
+      const float* srow = s_tile + (size_t)((r * S + ky) * WP + xu * WO * S) * DWT_CC + lane;
 #pragma unroll
-      for (int px = 0; px < WP; ++px) {
+      for (int px = 0; px < UP; ++px) {
         const float v = srow[px * DWT_CC];
 #pragma unroll
         for (int kx = 0; kx < KS; ++kx) {
@@ -83,7 +86,7 @@ k_dw_tile(const float* __restrict__ in, const float* __restrict__ w /*[KS*KS][C]
         }
       }
     }
-    float* orow = out + ((size_t)(b * Ho + oy0 + r) * WO) * C + c;
+    float* orow = out + ((size_t)(b * Ho + oy0 + r) * Wo + ox0 + xu * WO) * C + c;
 #pragma unroll
     for (int x = 0; x < WO; ++x) {
       const float o = swishf(acc[x] + bv);
@@ -112,7 +115,7 @@ k_dw_tile(const float* __restrict__ in, const float* __restrict__ w /*[KS*KS][C]
         a = fmaf(wv.x, m.x, fmaf(wv.y, m.y, fmaf(wv.z, m.z, fmaf(wv.w, m.w, a))));
       }
     }
-    partial_r[(((size_t)b * n_strips + strip) * gridDim.x + blockIdx.x) * Cse + tid] = a;
+    partial_r[(((size_t)b * n_strips + blockIdx.y) * gridDim.x + blockIdx.x) * Cse + tid] = a;
   }
 }
 
@@ -168,19 +171,23 @@ k_se_fc2(const float* __restrict__ partial_r, int n_part /*strips * chunks*/, in
 }
 
 // ---- host side -------------------------------------------------------------------------------------------
-struct DwTilePlan { bool ok; int R, n_strips, n_chunks, smem_bytes; };
+struct DwTilePlan { bool ok; int R, n_strips, n_xt, wo, xu, n_chunks, smem_bytes; };
 
 inline DwTilePlan dw_tile_plan(const BlockSpec& b) {
   DwTilePlan p{};
   p.ok = false;
-  if (b.hout > 30) return p;
   if (!((b.k == 3 || b.k == 5) && (b.s == 1 || b.s == 2))) return p;
-  if (!(b.wout == 40 || b.wout == 20 || b.wout == 10)) return p;
-  if (b.wout == 40 && b.s != 1) return p;   // the 60x80 -> 30x40 stride-2 block keeps the rolling kernel
-  // strips: whole image when it fits ~60 KB, else rows of ~10
+  // instances (launch_dw_tile): unit width x units per tile row
+  if (b.wout == 10) { p.wo = 10; p.xu = 1; }
+  else if (b.wout == 20) { p.wo = 20; p.xu = 1; }
+  else if (b.wout == 40 && b.k == 5 && b.s == 1) { p.wo = 40; p.xu = 1; }
+  else return p;   // the 120x160 and 60x80 blocks keep the rolling kernel (measured: the tiled kernel is slower there)
+  const int tile_w = p.wo * p.xu;
+  p.n_xt = b.wout / tile_w;
+  auto smem = [&](int R) { return ((R - 1) * b.s + b.k) * ((tile_w - 1) * b.s + b.k) * DWT_CC * 4; };
+  const int limit = 80 * 1024;
   p.R = b.hout;
-  auto smem = [&](int R) { return ((R - 1) * b.s + b.k) * ((b.wout - 1) * b.s + b.k) * DWT_CC * 4; };
-  while (smem(p.R) > 80 * 1024 && p.R > 1) p.R = (p.R + 1) / 2;
+  while (smem(p.R) > limit && p.R > 1) p.R = (p.R + 1) / 2;
   p.n_strips = (b.hout + p.R - 1) / p.R;
   p.R = (b.hout + p.n_strips - 1) / p.n_strips;
   p.n_chunks = (b.cexp + DWT_CC - 1) / DWT_CC;

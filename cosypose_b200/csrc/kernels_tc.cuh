@@ -27,8 +27,6 @@
 //   * 4 drain warps (warp w owns TMEM lanes 32(w%4)..+31 = output rows) add every stage's partial
 //     sums into registers and finally apply bias / swish / residual and store 16-byte vectors.
 #pragma once
-#include <cuda.h>
-
 #include "common.h"
 #include "kernels_backbone.cuh"
 
@@ -77,25 +75,27 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "}\n" ::"r"(bar), "r"(parity)
       : "memory");
 }
-// Whole-warp wait: lane 0 polls, the other lanes park at the warp barrier.  When all 32 lanes spin on the
-// barrier they leave the loop on different polls and nothing makes them reconverge before the .sync.aligned
-// tcgen05.st / tcgen05.ld that follow; with TMA-fed stages (waits that really spin) the first rows of a tile
-// were then occasionally written to TMEM by a split warp and lost (tools/dbg_determinism.py found it).
+// Whole-warp wait with a warp-uniform exit: every lane polls (its own acquire) and the loop ends on a warp
+// vote, so the lanes never leave the loop on different polls.  (When all 32 lanes spin independently nothing
+// makes them reconverge before the .sync.aligned tcgen05.st / tcgen05.ld / elect.sync that follow.)
 __device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {
-  if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity);
-  __syncwarp();
+  asm volatile(
+      "{\n"
+      ".reg .pred p, q;\n"
+      "VWAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "vote.sync.all.pred q, p, 0xffffffff;\n"
+      "@q bra VWAIT_DONE;\n"
+      "nanosleep.u32 20;\n"
+      "bra VWAIT_LOOP;\n"
+      "VWAIT_DONE:\n"
+      "}\n" ::"r"(bar), "r"(parity)
+      : "memory");
 }
 __device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
-}
-// 2-D tiled TMA load (box = BK x BM floats, 128-byte swizzle) completing on an mbarrier
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
-      "l"(tm), "r"(c0), "r"(c1), "r"(bar)
-      : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -199,8 +199,8 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
-constexpr int RAW_DEPTH = 2;                       // raw A k-stages in flight per producer group
-constexpr int RAW_ROW_BYTES = BK * 4;              // 128: one swizzle-128B row of the TMA box
+constexpr int RAW_DEPTH = 2;                       // raw A k-stages in flight per CTA (two CTAs per SM)
+constexpr int RAW_ROW_BYTES = BK * 4 + 16;         // 144: row pitch that keeps 16-byte row reads conflict free
 constexpr int RAW_STAGE_BYTES = BM * RAW_ROW_BYTES;
 // Warp-uniform issue: every lane executes the instruction slot, one lane (pred != 0) performs it.  With
 // a divergent `if (lane == 0)` around it the compiler cannot keep the operands in uniform registers and
@@ -256,7 +256,7 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
 // alternate k-stages (for layers with fewer tiles than CTA slots, where a second CTA per SM would sit empty).
 template <int BN_MAX, bool GATE, bool SWISH, bool RESID, int NG>
 __global__ void __launch_bounds__(threads_for(NG), NG == 1 ? 2 : 1)
-k_pw_gemm_tc(const __grid_constant__ CUtensorMap tmA, const float* __restrict__ A, const float* __restrict__ Wpk, const float* __restrict__ bias,
+k_pw_gemm_tc(const float* __restrict__ A, const float* __restrict__ Wpk, const float* __restrict__ bias,
              const float* __restrict__ gate, const float* __restrict__ resid, float* __restrict__ C, int M, int N,
              int K, int rows_per_img, int bn, int n_tiles, int nb, int resident) {
   constexpr int N_GROUPS = NG;
@@ -265,7 +265,7 @@ k_pw_gemm_tc(const __grid_constant__ CUtensorMap tmA, const float* __restrict__ 
   constexpr int LOADER_WARP = DRAIN_WARP0 + 4;
   constexpr int RAW_BYTES = raw_bytes(NG);
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[2 * N_ASLOTS + 2 * MAX_BSLOTS + 4 + 2 * NG * RAW_DEPTH];
+  __shared__ __align__(8) uint64_t bars[2 * N_ASLOTS + 2 * MAX_BSLOTS + 4];
   __shared__ uint32_t s_tmem;
   __shared__ __align__(16) float s_bias[64];          // bias of this CTA's n-tile (fixed for the CTA's lifetime)
   constexpr uint32_t TMEM_COLS = 256;               // two CTAs per SM share the 512 columns
@@ -288,10 +288,6 @@ k_pw_gemm_tc(const __grid_constant__ CUtensorMap tmA, const float* __restrict__ 
   auto emptyB = [&](int s) { return smem_u32(&bars[2 * N_ASLOTS + MAX_BSLOTS + s]); };
   auto acc_full = [&](int b) { return smem_u32(&bars[2 * N_ASLOTS + 2 * MAX_BSLOTS + b]); };
   auto acc_empty = [&](int b) { return smem_u32(&bars[2 * N_ASLOTS + 2 * MAX_BSLOTS + 2 + b]); };
-  auto fullRaw = [&](int grp, int rs) { return smem_u32(&bars[2 * N_ASLOTS + 2 * MAX_BSLOTS + 4 + grp * RAW_DEPTH + rs]); };
-  auto emptyRaw = [&](int grp, int rs) {
-    return smem_u32(&bars[2 * N_ASLOTS + 2 * MAX_BSLOTS + 4 + NG * RAW_DEPTH + grp * RAW_DEPTH + rs]);
-  };
 
   if (tid == 0) trace(0);
   if (tid == 0) {
@@ -307,11 +303,6 @@ k_pw_gemm_tc(const __grid_constant__ CUtensorMap tmA, const float* __restrict__ 
       mbar_init(acc_full(b), 1);
       mbar_init(acc_empty(b), DRAIN_THREADS);
     }
-    for (int gq = 0; gq < NG; ++gq)
-      for (int rs = 0; rs < RAW_DEPTH; ++rs) {
-        mbar_init(fullRaw(gq, rs), 1);
-        mbar_init(emptyRaw(gq, rs), PRODUCER_THREADS);
-      }
     fence_barrier_init();
   }
   if (tid < 64) {
@@ -327,28 +318,50 @@ k_pw_gemm_tc(const __grid_constant__ CUtensorMap tmA, const float* __restrict__ 
 
   if (warp < MMA_WARP) {
     // ------------------------------------------------------------------ producers (A operand)
-    // Raw fp32 rows arrive by TMA (one 32 x 128 box per k-stage, 128-byte swizzle, issued by the loader warp
-    // RAW_DEPTH stages ahead; rows beyond M and columns beyond K come back as zeros); each thread reads ITS
-    // tile row back (the swizzle spreads 8 consecutive rows over all banks), applies the SE gate, splits
-    // hi/lo, hands the slot back and writes both halves to its TMEM lane.
+    // Raw fp32 rows travel global -> shared by cp.async (coalesced: 4 full rows per warp request,
+    // RAW_DEPTH k-stages in flight per group, no register scoreboard involved); each thread then
+    // reads ITS tile row back (144-byte pitch: conflict free), applies the SE gate, splits hi/lo
+    // and writes both halves to its TMEM lane.
     const int grp = warp / 4, q = warp % 4, tg = tid % PRODUCER_THREADS;
     const int row = q * 32 + lane;                  // tile row == TMEM lane written by this thread
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
     const uint32_t ring = raw_base + grp * RAW_DEPTH * RAW_STAGE_BYTES;
-    const int n_mine = n_items > grp ? (n_items - 1 - grp) / N_GROUPS + 1 : 0;   // items g = grp + NG i
+    const int n_mine = n_items > grp ? (n_items - 1 - grp) / N_GROUPS + 1 : 0;   // items g = grp + 2 i
+    auto issue_raw = [&](int i) {
+      if (i < n_mine) {
+        const int g = grp + i * N_GROUPS;
+        const int m0 = (m_first + (g / nk) * m_step) * BM, k0 = (g % nk) * BK;
+        const uint32_t slot = ring + (i % RAW_DEPTH) * RAW_STAGE_BYTES;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int c = it * PRODUCER_THREADS + tg, r = c >> 3, kc = c & 7;
+          const int m = m0 + r, k = k0 + kc * 4;
+          const bool ok = m < M && k < K;
+          cp_async16(slot + r * RAW_ROW_BYTES + kc * 16, ok ? (const void*)(A + (size_t)m * K + k) : (const void*)A, ok);
+        }
+      }
+      cp_async_commit();   // one group per item, also when empty, so wait_group counts stay aligned
+    };
+#pragma unroll
+    for (int i = 0; i < RAW_DEPTH - 1; ++i) issue_raw(i);
     for (int i = 0; i < n_mine; ++i) {
       const int g = grp + i * N_GROUPS;
       const int m = (m_first + (g / nk) * m_step) * BM + row, k0 = (g % nk) * BK;
       const int slot = g % N_ASLOTS;
-      const int rs = i % RAW_DEPTH;
       const bool tr = tg == 0 && g == 6;
-      mbar_wait_warp(fullRaw(grp, rs), (i / RAW_DEPTH) & 1);
-      const uint32_t src = ring + rs * RAW_STAGE_BYTES + row * RAW_ROW_BYTES;
+      if (tr) trace(8);
+      cp_async_wait<RAW_DEPTH - 2>();               // this thread's copies of item i have landed
+      if (tr) trace(9);
+      named_bar_sync(1 + grp, PRODUCER_THREADS);    // ... and everybody else's; slot (i-1) is free again
+      if (tr) trace(10);
+      issue_raw(i + RAW_DEPTH - 1);
+      if (tr) trace(11);
+      const uint32_t src = ring + (i % RAW_DEPTH) * RAW_STAGE_BYTES + row * RAW_ROW_BYTES;
       float v[BK];
 #pragma unroll
       for (int c = 0; c < BK / 4; ++c)
         asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[c * 4]), "=f"(v[c * 4 + 1]), "=f"(v[c * 4 + 2]), "=f"(v[c * 4 + 3])
-                     : "r"(src + ((c ^ (row & 7)) << 4)) : "memory");
+                     : "r"(src + c * 16) : "memory");
       if (GATE) {
         const float* gsrc = gate + (size_t)(min(m, M - 1) / rows_per_img) * K + k0;
 #pragma unroll
@@ -367,7 +380,6 @@ k_pw_gemm_tc(const __grid_constant__ CUtensorMap tmA, const float* __restrict__ 
         v[c] = h;
       }
       if (tr) trace(12);
-      mbar_arrive(emptyRaw(grp, rs));               // all values consumed: the slot may be refilled
       if (g >= N_ASLOTS) mbar_wait_warp(acc_full(slot), ((g / N_ASLOTS) - 1) & 1);   // MMAs of item g-2 done
       tc_fence_after();
       if (tr) trace(13);
@@ -379,6 +391,7 @@ k_pw_gemm_tc(const __grid_constant__ CUtensorMap tmA, const float* __restrict__ 
       mbar_arrive(fullA(slot));
       if (tr) trace(15);
     }
+    cp_async_wait<0>();
   } else if (warp == MMA_WARP) {
     // ------------------------------------------------------------------ MMA issuer
     const uint32_t idesc = make_idesc(bn);
@@ -416,22 +429,15 @@ k_pw_gemm_tc(const __grid_constant__ CUtensorMap tmA, const float* __restrict__ 
     }
     tc_fence_before();
   } else if (warp == LOADER_WARP) {
-    // ------------------------------------------------------------------ loader: B (bulk copies) and raw A (TMA)
+    // ------------------------------------------------------------------ B loader
     if (lane == 0) {
       const float* wsrc = Wpk + (size_t)n_tile * nk * (2 * bsb / 4);
-      for (int g = 0; g < n_items; ++g) {
-        const int s = g % nk;
-        if (!resident || g < nk) {
-          const int bslot = resident ? s : g % nb;
-          if (!resident && g >= nb) mbar_wait(emptyB(bslot), ((g / nb) - 1) & 1);
-          mbar_arrive_expect_tx(fullB(bslot), 2 * bsb);
-          bulk_copy_g2s(b_base + bslot * 2 * bsb, wsrc + (size_t)s * (2 * bsb / 4), 2 * bsb, fullB(bslot));
-        }
-        const int grp = g % N_GROUPS, i = g / N_GROUPS, rs = i % RAW_DEPTH;
-        if (i >= RAW_DEPTH) mbar_wait(emptyRaw(grp, rs), ((i / RAW_DEPTH) - 1) & 1);
-        mbar_arrive_expect_tx(fullRaw(grp, rs), RAW_STAGE_BYTES);
-        tma_load_2d(raw_base + (grp * RAW_DEPTH + rs) * RAW_STAGE_BYTES, &tmA, s * BK,
-                    (m_first + (g / nk) * m_step) * BM, fullRaw(grp, rs));
+      const int n_loads = resident ? min(nk, n_items) : n_items;
+      for (int g = 0; g < n_loads; ++g) {
+        const int s = g % nk, bslot = resident ? s : g % nb;
+        if (!resident && g >= nb) mbar_wait(emptyB(bslot), ((g / nb) - 1) & 1);
+        mbar_arrive_expect_tx(fullB(bslot), 2 * bsb);
+        bulk_copy_g2s(b_base + bslot * 2 * bsb, wsrc + (size_t)s * (2 * bsb / 4), 2 * bsb, fullB(bslot));
       }
     }
   } else {
@@ -521,18 +527,6 @@ k_pw_gemm_tc(const __grid_constant__ CUtensorMap tmA, const float* __restrict__ 
     tmem_dealloc(tmem_base, TMEM_COLS);
   }
   if (tid == 0) trace(3);
-}
-
-// ---- host side: tensor map of the A operand --------------------------------------------------------
-// A [M][K] fp32 row-major; box = BK columns x BM rows, 128-byte swizzle, zero fill outside the tensor.
-inline bool make_a_tensor_map(CUtensorMap* tm, const float* A, int M, int K) {
-  cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)M};
-  cuuint64_t gstride[1] = {(cuuint64_t)K * 4};
-  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
-  cuuint32_t estr[2] = {1, 1};
-  return cuTensorMapEncodeTiled(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(A), gdim, gstride, box, estr,
-                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 // ---- host side: tile plan and weight packing -------------------------------------------------------
