@@ -135,8 +135,9 @@ static int launch_gemm_tc(bool gate, bool swish, bool resid, const float* A, con
                           cudaStream_t st) {
   const tc::Plan p1 = tc::make_plan(N, K, 1);
   const int tiles = ((M + tc::BM - 1) / tc::BM) * p1.n_tiles;
-  // fewer tiles than two-per-SM CTA slots: one bigger CTA per SM with two producer groups
-  const int ng = g_tc_groups ? g_tc_groups : (tiles <= 296 ? 2 : 1);
+  // no more tiles than SMs: one bigger CTA per SM with two producer groups (measured at 140 tiles: 52 vs 65 us;
+  // at 210 tiles the 296 two-per-SM slots finish in one round and win, 73 vs 86 us)
+  const int ng = g_tc_groups ? g_tc_groups : (tiles <= 148 ? 2 : 1);
 #define TC_ARGS A, Wpk, bias, g, r, C, M, N, K, rows_per_img, st
 #define TC_DISPATCH(G, S, R) (ng == 2 ? launch_gemm_tc_inst<64, G, S, R, 2>(TC_ARGS) : launch_gemm_tc_inst<64, G, S, R, 1>(TC_ARGS))
   if (!gate && swish && !resid) return TC_DISPATCH(false, true, false);
