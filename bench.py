@@ -59,9 +59,53 @@ def kernel_algorithmic_bytes():
     return out
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures
-# (profiles/README.md), keyed by kernel category; None where no capture exists
-NCU_TRAFFIC_NOTE = 'profiles/README.md'
+# DRAM traffic of the tensor-core 1x1 kernel from the committed `ncu --set full` capture
+# (profiles/r01b_ncu_full_blocks0to4.csv: the 7 k_pw_gemm_tc launches of blocks 0-4, 64 hypotheses):
+# sum of dram__bytes_read.sum + dram__bytes_write.sum against the algorithmic bytes of the same launches.
+NCU_GEMM_CAPTURE = dict(launches=7, dram_bytes=2313.1e6, algorithmic_bytes=2575.8e6,
+                        source='profiles/r01b_ncu_full_blocks0to4.csv')
+GEMM_CATS = ('expand_1x1', 'project_1x1', 'head_1x1')
+
+
+def roofline_object(prof, prof_steps, fwd_per_step, peak, peak_src):
+    """`roofline` of the JSON line.  Dominant kernel = k_pw_gemm_tc (every 1x1 convolution: expand, project,
+    head; ~58 % of the step).  achieved = algorithmic bytes of its launches / their CUDA-event device time
+    (engine profiling mode brackets every launch with events on the launching stream); `trunk` is the
+    whole-network figure of SURVEY.md section 8(d) (block-boundary activations only, i.e. what a fully fused
+    trunk would move); by_kernel_* give every category against its own one-kernel-per-stage byte count."""
+    kbytes = kernel_algorithmic_bytes()
+    ms = {c: prof[c][1] / prof_steps for c in prof}                 # device ms per step and category
+    n_launch = {c: prof[c][0] / prof_steps for c in prof}
+    by_kernel_gbs = {c: round(fwd_per_step * kbytes[c] / (ms[c] * 1e-3) / 1e9, 1) for c in kbytes if ms[c] > 0}
+    gemm_ms = sum(ms[c] for c in GEMM_CATS)
+    gemm_bytes = fwd_per_step * sum(kbytes[c] for c in GEMM_CATS)
+    gemm_launches = sum(n_launch[c] for c in GEMM_CATS)
+    achieved = gemm_bytes / (gemm_ms * 1e-3) / 1e9 if gemm_ms > 0 else None
+    backbone_cats = ('stem', 'expand_1x1', 'depthwise', 'squeeze_excite', 'project_1x1', 'head_1x1', 'pool_fc_update')
+    bb_ms = sum(ms[c] for c in backbone_cats)
+    trunk = fwd_per_step * ALGO_BYTES_PER_FORWARD / (bb_ms * 1e-3) / 1e9 if bb_ms > 0 else None
+    tot = sum(ms.values())
+    per_launch = gemm_bytes / gemm_launches if gemm_launches else None
+    ratio = NCU_GEMM_CAPTURE['dram_bytes'] / NCU_GEMM_CAPTURE['algorithmic_bytes']
+    return {
+        'bound': 'hbm', 'kernel': 'k_pw_gemm_tc (tcgen05 3xTF32 1x1 convolutions: expand + project + head)',
+        'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak if achieved else None,
+        'peak_source': peak_src,
+        'traffic': per_launch * ratio if per_launch else None,
+        'traffic_note': f"mean algorithmic bytes per launch x {ratio:.3f}, the DRAM/algorithmic ratio ncu measured on "
+                        f"{NCU_GEMM_CAPTURE['launches']} launches ({NCU_GEMM_CAPTURE['source']})",
+        'algorithmic_bytes_per_launch': per_launch, 'launches_per_step': gemm_launches,
+        'launch_us': gemm_ms * 1e3 / gemm_launches if gemm_launches else None,
+        'share_of_step': gemm_ms / tot if tot > 0 else None,
+        'trunk': {'kernel': 'EfficientNet-B3 trunk forward (stem + 26 MBConv + head), all launches',
+                  'achieved': trunk, 'frac': trunk / peak if trunk else None, 'ms_per_step': bb_ms,
+                  'algorithmic_bytes_per_step': fwd_per_step * ALGO_BYTES_PER_FORWARD,
+                  'tflops': fwd_per_step * ALGO_FLOP_PER_FORWARD / (bb_ms * 1e-3) / 1e12 if bb_ms > 0 else None},
+        'by_kernel_gbs': by_kernel_gbs,
+        'by_kernel_frac': {c: round(v / peak, 4) for c, v in by_kernel_gbs.items()},
+        'by_kernel_ms_per_step': {c: round(v, 4) for c, v in ms.items() if v > 0},
+        'by_kernel_share': {c: round(v / tot, 4) for c, v in ms.items() if v > 0},
+    }
 
 
 def workload_config(world):
@@ -272,14 +316,6 @@ def main():
         value = hyps / (ms_total * 1e-3)
         fwd_per_step = w.n * (N_COARSE + N_REFINE)
         peak, peak_src = measured_peaks()
-        backbone_cats = ('stem', 'expand_1x1', 'depthwise', 'squeeze_excite', 'project_1x1', 'head_1x1', 'pool_fc_update')
-        bb_ms = sum(prof[c][1] for c in backbone_cats) / prof_steps          # per step, this rank
-        achieved = fwd_per_step * ALGO_BYTES_PER_FORWARD / (bb_ms * 1e-3) / 1e9 if bb_ms > 0 else None
-        tot_prof = sum(ms for _, ms in prof.values())
-        kbytes = kernel_algorithmic_bytes()
-        by_kernel_gbs = {c: round(fwd_per_step * kbytes[c] / (prof[c][1] / prof_steps * 1e-3) / 1e9, 1)
-                         for c in kbytes if prof[c][1] > 0}
-        dominant = max(kbytes, key=lambda c: prof[c][1])
         line = dict(
             metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
             ms_per_step=ms_total / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
@@ -289,21 +325,7 @@ def main():
             e2e={'value': hyps / (ms_e2e * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': int(h2d),
                  'd2h_bytes_per_step': int(d2h), 'ms_per_step': ms_e2e / args.steps},
             gpu_launches=int(launches),
-            roofline={'bound': 'hbm', 'kernel': 'EfficientNet-B3 trunk forward (stem + 26 MBConv + head), all launches',
-                      'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak if achieved else None,
-                      'peak_source': peak_src, 'traffic': None,
-                      'algorithmic_bytes_per_launch': fwd_per_step * ALGO_BYTES_PER_FORWARD,
-                      'launch_ms': bb_ms,
-                      'tflops': fwd_per_step * ALGO_FLOP_PER_FORWARD / (bb_ms * 1e-3) / 1e12 if bb_ms > 0 else None,
-                      'dominant_kernel': {'category': dominant, 'achieved': by_kernel_gbs[dominant],
-                                          'frac': round(by_kernel_gbs[dominant] / peak, 4), 'unit': 'GB/s',
-                                          'algorithmic_bytes_per_step': int(fwd_per_step * kbytes[dominant]),
-                                          'launches_per_step': int(prof[dominant][0] / prof_steps),
-                                          'traffic': NCU_TRAFFIC_NOTE},
-                      'by_kernel_gbs': by_kernel_gbs,
-                      'by_kernel_frac': {c: round(v / peak, 4) for c, v in by_kernel_gbs.items()},
-                      'by_kernel_ms_per_step': {c: round(ms / prof_steps, 4) for c, (_, ms) in prof.items() if ms > 0},
-                      'by_kernel_share': {c: round(ms / tot_prof, 4) for c, (_, ms) in prof.items() if ms > 0}},
+            roofline=roofline_object(prof, prof_steps, fwd_per_step, peak, peak_src),
         )
         if world == 1 and not args.no_cpu_baseline:
             cb, _ = cpu_reference(1, 1, sample_hyps=args.cpu_sample)

@@ -149,3 +149,33 @@ def test_engine_fails_loudly_without_gpu():
     from cosypose_b200.engine import Engine
     with pytest.raises(_lib.EngineError):
         Engine(0)
+
+
+def test_bench_roofline_object():
+    """bench.py's `roofline` object from a recorded engine profile (no GPU): the dominant kernel is the tensor-core
+    1x1 kernel, fractions are consistent with their numerators, the whole-trunk figure uses SURVEY 8(d)'s bytes."""
+    import importlib.util
+    import json
+    from pathlib import Path
+    root = Path(__file__).resolve().parents[1]
+    spec = importlib.util.spec_from_file_location('bench_mod', root / 'bench.py')
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    kb = bench.kernel_algorithmic_bytes()
+    assert abs(sum(kb.values()) / 1e6 - 164.5) < 0.1          # one-kernel-per-stage bytes per forward
+    assert bench.ALGO_BYTES_PER_FORWARD == 6107136 * 4        # SURVEY.md section 8(d)
+    # (launches, ms) over 5 profiled steps, the shape engine.profile_read() returns
+    prof = {'geometry': (25, 0.5), 'roi_crop': (25, 3.15), 'stem': (25, 8.3), 'expand_1x1': (625, 38.6),
+            'depthwise': (650, 43.4), 'squeeze_excite': (650, 7.1), 'project_1x1': (650, 50.9),
+            'head_1x1': (25, 1.45), 'pool_fc_update': (25, 0.83), 'ransac': (0, 0.0)}
+    r = bench.roofline_object(prof, 5, 320, 6537.0, 'measured (MEASURED_PEAKS.json)')
+    json.dumps(r)
+    assert r['bound'] == 'hbm' and r['unit'] == 'GB/s' and 'k_pw_gemm_tc' in r['kernel']
+    gemm_ms = (38.6 + 50.9 + 1.45) / 5
+    want = 320 * (kb['expand_1x1'] + kb['project_1x1'] + kb['head_1x1']) / (gemm_ms * 1e-3) / 1e9
+    assert abs(r['achieved'] - want) < 1e-6 * want and abs(r['frac'] - want / 6537.0) < 1e-9
+    assert r['launches_per_step'] == 260 and 0.5 < r['share_of_step'] < 0.7
+    assert 0.8 < r['traffic'] / r['algorithmic_bytes_per_launch'] <= 1.0
+    assert abs(r['trunk']['achieved'] - 320 * 6107136 * 4 / (sum(prof[c][1] for c in prof if c not in
+               ('geometry', 'roi_crop', 'ransac')) / 5 * 1e-3) / 1e9) < 1e-3
+    assert set(r['by_kernel_gbs']) == {'stem', 'expand_1x1', 'depthwise', 'project_1x1', 'head_1x1'}
