@@ -129,8 +129,14 @@ int cosyb200_refine_n(cosyb200_handle* h, int slot, int B, int n_iter, const flo
                       int render_u8, const float* TCO_in_dev, float* TCO_out_dev, float* K_crop_dev,
                       float* boxes_rend_dev, float* boxes_crop_dev, float* pose9_dev, void* stream);
 
-/* Engine options.  "gemm_impl": 1 (default) runs the 1x1 convolutions on the tcgen05 tensor cores
- * with the 3xTF32 split, 0 on CUDA cores in plain fp32 (kept as the per-block parity anchor). */
+/* Engine options (all choose between implementations of the same arithmetic; results agree within the
+ * tolerances of tests/test_gpu_*.py):
+ *   "gemm_impl": 1 (default) runs the 1x1 convolutions on the tcgen05 tensor cores with the 3xTF32 split,
+ *                0 on CUDA cores in plain fp32 (kept as the per-block parity anchor);
+ *   "dw_impl":   1 (default) shared-memory tiled depthwise + split squeeze-excite for the blocks with
+ *                output <= 30x40, 0 = rolling-window depthwise + k_se_gate everywhere;
+ *   "tc_groups": 0 (default) picks the tensor-core kernel variant per layer, 1 / 2 force one / two
+ *                producer warpgroups (process-wide). */
 int cosyb200_set_option(cosyb200_handle* h, const char* name, int value);
 
 /* One 1x1 convolution on caller data, for kernel-level tests (reference: the Conv2d 1x1 + folded
