@@ -105,6 +105,9 @@ static void launch_gemm(bool gate, bool swish, bool resid, const float* A, const
 
 // tensor-core path: Wpk = tc::pack_weights image of the [N][K] weight
 static int g_tc_groups = 0;   // 0: pick per layer, 1 / 2: force the producer-group variant (set_option "tc_groups")
+// No more tiles than SMs: one bigger CTA per SM with two producer groups (measured at 140 tiles: 52 vs 65 us; at
+// 210 tiles the 296 two-per-SM slots finish in one round and win, 73 vs 86 us).
+static int tc_groups_for(int tiles) { return tiles <= 148 ? 2 : 1; }
 template <int BN_MAX, bool G, bool S, bool R, int NG>
 static int launch_gemm_tc_inst(const float* A, const float* Wpk, const float* bias, const float* g,
                                const float* r, float* C, int M, int N, int K, int rows_per_img, cudaStream_t st) {
@@ -135,9 +138,7 @@ static int launch_gemm_tc(bool gate, bool swish, bool resid, const float* A, con
                           cudaStream_t st) {
   const tc::Plan p1 = tc::make_plan(N, K, 1);
   const int tiles = ((M + tc::BM - 1) / tc::BM) * p1.n_tiles;
-  // no more tiles than SMs: one bigger CTA per SM with two producer groups (measured at 140 tiles: 52 vs 65 us;
-  // at 210 tiles the 296 two-per-SM slots finish in one round and win, 73 vs 86 us)
-  const int ng = g_tc_groups ? g_tc_groups : (tiles <= 148 ? 2 : 1);
+  const int ng = g_tc_groups ? g_tc_groups : tc_groups_for(tiles);
 #define TC_ARGS A, Wpk, bias, g, r, C, M, N, K, rows_per_img, st
 #define TC_DISPATCH(G, S, R) (ng == 2 ? launch_gemm_tc_inst<64, G, S, R, 2>(TC_ARGS) : launch_gemm_tc_inst<64, G, S, R, 1>(TC_ARGS))
   if (!gate && swish && !resid) return TC_DISPATCH(false, true, false);
@@ -345,6 +346,32 @@ int cosyb200_effnet_block(int idx, int32_t* out) {
   CB_CHECK_ARG(out != nullptr && idx >= 0 && idx < (int)blocks.size(), "effnet_block: bad index %d", idx);
   const BlockSpec& b = blocks[idx];
   int32_t v[11] = {b.k, b.s, b.e, b.cin, b.cexp, b.cse, b.cout, b.pad_lo, b.pad_hi, b.skip, (int32_t)blocks.size()};
+  memcpy(out, v, sizeof(v));
+  return COSYB200_OK;
+}
+
+int cosyb200_launch_plan(int idx, int batch, int32_t* out) {
+  static const std::vector<BlockSpec> blocks = make_effnet_b3();
+  CB_CHECK_ARG(out != nullptr && idx >= 0 && idx < (int)blocks.size() && batch >= 1, "launch_plan: bad arguments");
+  const BlockSpec& b = blocks[idx];
+  const DwPlan rp = dw_plan(b);
+  const DwTilePlan tp = dw_tile_plan(b);
+  const int Min = batch * b.hin * b.win, Mout = batch * b.hout * b.wout;
+  const tc::Plan pe = tc::make_plan(b.cexp, b.cin, 1), pp = tc::make_plan(b.cout, b.cexp, 1);
+  const int tiles_e = ((Min + tc::BM - 1) / tc::BM) * pe.n_tiles, tiles_p = ((Mout + tc::BM - 1) / tc::BM) * pp.n_tiles;
+  const int ng_e = tc_groups_for(tiles_e), ng_p = tc_groups_for(tiles_p);
+  const tc::Plan pe2 = tc::make_plan(b.cexp, b.cin, ng_e), pp2 = tc::make_plan(b.cout, b.cexp, ng_p);
+  int32_t v[32] = {
+      // depthwise: 0 tiled?, 1 rows per tile, 2 row strips, 3 x tiles, 4 unit width, 5 units per row, 6 channel chunks,
+      // 7 shared memory bytes; rolling kernel: 8 tiles, 9 channel chunks, 10 threads, 11 rows per tile
+      tp.ok ? 1 : 0, tp.R, tp.n_strips, tp.n_xt, tp.wo, tp.xu, tp.n_chunks, tp.smem_bytes,
+      rp.tiles, rp.n_chunks, rp.Gc * rp.P, rp.TH,
+      // expand 1x1: 12 bn, 13 n tiles, 14 k stages, 15 weight slots, 16 resident, 17 shared memory bytes, 18 producer
+      // groups, 19 tiles
+      pe2.bn, pe2.n_tiles, pe2.nk, pe2.nb, pe2.resident, pe2.smem_bytes, ng_e, tiles_e,
+      // project 1x1: 20..27 the same
+      pp2.bn, pp2.n_tiles, pp2.nk, pp2.nb, pp2.resident, pp2.smem_bytes, ng_p, tiles_p,
+      0, 0, 0, 0};
   memcpy(out, v, sizeof(v));
   return COSYB200_OK;
 }

@@ -51,6 +51,14 @@ int cosyb200_destroy(cosyb200_handle* h);
  * pad_lo,pad_hi,skip,n_blocks (reference: models/efficientnet_utils.py:59-81,123-146,259-264). */
 int cosyb200_effnet_block(int idx, int32_t* out11);
 
+/* Launch configuration the engine uses for MBConv block `idx` at `batch` hypotheses (host code only, no GPU
+ * needed; tests/test_host_logic.py checks the resource budgets): out[32] =
+ *   [0..7]   tiled depthwise: used, rows per tile, row strips, x tiles, unit width, units per row, channel chunks,
+ *            dynamic shared memory bytes;  [8..11] rolling depthwise: tiles, channel chunks, threads, rows per tile;
+ *   [12..19] expand 1x1 (tensor cores): n tile width, n tiles, k stages, weight slots, resident, dynamic shared
+ *            memory bytes, producer groups, output tiles;  [20..27] project 1x1: the same. */
+int cosyb200_launch_plan(int idx, int batch, int32_t* out32);
+
 /* Replaces PosePredictor.load_state_dict (reference: models/pose.py:18-36, weights named as in
  * SURVEY.md section 5).  `names[i]` is a state_dict key, `ptrs_host[i]` its fp32 data, `numels[i]`
  * its element count.  BatchNorm (eps 1e-3) is folded into the conv weights here. */

@@ -179,3 +179,45 @@ def test_bench_roofline_object():
     assert abs(r['trunk']['achieved'] - 320 * 6107136 * 4 / (sum(prof[c][1] for c in prof if c not in
                ('geometry', 'roi_crop', 'ransac')) / 5 * 1e-3) / 1e9) < 1e-3
     assert set(r['by_kernel_gbs']) == {'stem', 'expand_1x1', 'depthwise', 'project_1x1', 'head_1x1'}
+
+
+def test_launch_plans_fit_the_sm():
+    """Resource budgets of every launch configuration at the benchmark batch and at batch 1 (host code of the
+    engine, no GPU): shared memory per SM (227 KB), TMEM columns, tile coverage, thread counts."""
+    import ctypes
+    from cosypose_b200 import _lib, effnet_spec as spec
+    L = _lib.lib()
+    out = (ctypes.c_int32 * 32)()
+    SM_SMEM = 227 * 1024
+    shapes = spec.activation_shapes()
+    for batch in (1, 64, 4096):
+        for b, (_, hi, wi, _), (_, ho, wo, _) in zip(spec.BLOCKS, shapes[1:-2], shapes[2:-1]):
+            assert L.cosyb200_launch_plan(b.idx, batch, out) == 0
+            v = list(out)
+            tiled, R, n_strips, n_xt, wo_u, xu, n_chunks, smem = v[0:8]
+            if tiled:
+                assert R * n_strips >= ho and R * (n_strips - 1) < ho          # strips cover the rows exactly once
+                assert wo_u * xu * n_xt == wo                                   # x tiles cover the columns
+                assert n_chunks * 32 >= b.cexp > (n_chunks - 1) * 32
+                halo = ((R - 1) * b.s + b.k) * ((wo_u * xu - 1) * b.s + b.k) * 32 * 4
+                assert smem == halo and smem + 2048 <= SM_SMEM
+                assert b.cse <= 128                                             # k_se_fc2's shared arrays
+                assert ho <= 30                                                 # the larger blocks keep the rolling kernel
+            else:
+                assert ho >= 60 or (b.k == 5 and b.s == 2 and wo == 40)
+            tiles, chunks, threads, th = v[8:12]
+            assert 32 <= threads <= 256 and tiles >= 1 and th >= 1
+            for off, N, K, M in ((12, b.cexp, b.cin, batch * hi * wi), (20, b.cout, b.cexp, batch * ho * wo)):
+                if off == 12 and b.e == 1:
+                    continue
+                bn, n_tiles, nk, nb, resident, gsmem, ng, gtiles = v[off:off + 8]
+                assert bn % 16 == 0 and 16 <= bn <= 64 and bn * n_tiles >= N    # UMMA N granularity at M = 128
+                assert nk * 32 >= K > (nk - 1) * 32
+                assert 2 <= nb <= 8 or (resident and nb == nk)
+                assert bool(resident) == (nk <= nb)
+                per_sm = 2 if ng == 1 else 1
+                assert per_sm * (gsmem + 1024) <= SM_SMEM                       # CTAs per SM x (dynamic + static)
+                assert 2 * 64 + 2 * 64 <= 256                                   # TMEM columns per CTA: 2 acc + 2 A slots
+                assert gtiles == -(-M // 128) * n_tiles
+                assert ng == (2 if gtiles <= 148 else 1)
+    assert L.cosyb200_launch_plan(26, 64, out) == _lib.EINVAL
