@@ -12,6 +12,7 @@
 #include "kernels_ransac.cuh"
 #include "kernels_ba.cuh"
 #include "kernels_tc.cuh"
+#include "kernels_tc_tma.cuh"
 #include "kernels_dwtile.cuh"
 
 namespace cosyb {
@@ -133,6 +134,38 @@ static int launch_gemm_tc_inst(const float* A, const float* Wpk, const float* bi
   return 0;
 }
 
+// EXPERIMENTAL opt-in variant with TMA-fed A stages (kernels_tc_tma.cuh; set_option "tc_tma" / "tc_dbg")
+static int g_tc_tma = 0, g_tc_dbg = 0;
+template <int BN_MAX, bool G, bool S, bool R, int NG>
+static int launch_gemm_tc_tma_inst(const float* A, const float* Wpk, const float* bias, const float* g,
+                                   const float* r, float* C, int M, int N, int K, int rows_per_img, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    CB_CUDA(cudaFuncSetAttribute(tc::k_pw_gemm_tc_tma<BN_MAX, G, S, R, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 NG == 1 ? 112 * 1024 : 202 * 1024));
+    attr_set = true;
+  }
+  static int n_sms = 0;
+  if (n_sms == 0) {
+    int dev = 0;
+    CB_CUDA(cudaGetDevice(&dev));
+    CB_CUDA(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const tc::Plan p = tc::make_plan_tma(N, K, NG);
+  const int m_tiles = (M + tc::BM - 1) / tc::BM;
+  const int slots = NG == 1 ? 2 * n_sms : n_sms;
+  const int grid = std::min(m_tiles, std::max(1, slots / p.n_tiles)) * p.n_tiles;
+  CUtensorMap tmA;
+  if (!tc::make_a_tensor_map(&tmA, A, M, K)) {
+    set_error("launch_gemm_tc_tma: cuTensorMapEncodeTiled failed (A=%p M=%d K=%d)", (const void*)A, M, K);
+    return COSYB200_ECUDA;
+  }
+  tc::k_pw_gemm_tc_tma<BN_MAX, G, S, R, NG><<<grid, tc::threads_for(NG), p.smem_bytes, st>>>(
+      tmA, A, Wpk, bias, g, r, C, M, N, K, rows_per_img, p.bn, p.n_tiles, p.nb, p.resident, g_tc_dbg);
+  CB_LAUNCH_CHECK();
+  return 0;
+}
+
 static int launch_gemm_tc(bool gate, bool swish, bool resid, const float* A, const float* Wpk, const float* bias,
                           const float* g, const float* r, float* C, int M, int N, int K, int rows_per_img,
                           cudaStream_t st) {
@@ -140,7 +173,9 @@ static int launch_gemm_tc(bool gate, bool swish, bool resid, const float* A, con
   const int tiles = ((M + tc::BM - 1) / tc::BM) * p1.n_tiles;
   const int ng = g_tc_groups ? g_tc_groups : tc_groups_for(tiles);
 #define TC_ARGS A, Wpk, bias, g, r, C, M, N, K, rows_per_img, st
-#define TC_DISPATCH(G, S, R) (ng == 2 ? launch_gemm_tc_inst<64, G, S, R, 2>(TC_ARGS) : launch_gemm_tc_inst<64, G, S, R, 1>(TC_ARGS))
+#define TC_DISPATCH(G, S, R)                                                                                      \
+  (g_tc_tma ? (ng == 2 ? launch_gemm_tc_tma_inst<64, G, S, R, 2>(TC_ARGS) : launch_gemm_tc_tma_inst<64, G, S, R, 1>(TC_ARGS)) \
+            : (ng == 2 ? launch_gemm_tc_inst<64, G, S, R, 2>(TC_ARGS) : launch_gemm_tc_inst<64, G, S, R, 1>(TC_ARGS)))
   if (!gate && swish && !resid) return TC_DISPATCH(false, true, false);
   if (gate && !swish && !resid) return TC_DISPATCH(true, false, false);
   if (gate && !swish && resid) return TC_DISPATCH(true, false, true);
@@ -727,6 +762,15 @@ int cosyb200_set_option(cosyb200_handle* h, const char* name, int value) {
   if (strcmp(name, "gemm_impl") == 0) {
     CB_CHECK_ARG(value == 0 || value == 1, "set_option: gemm_impl must be 0 (cuda cores) or 1 (tcgen05)");
     h->gemm_impl = value;
+    return COSYB200_OK;
+  }
+  if (strcmp(name, "tc_tma") == 0) {
+    CB_CHECK_ARG(value == 0 || value == 1, "set_option: tc_tma must be 0 (cp.async A stages) or 1 (experimental TMA A stages)");
+    g_tc_tma = value;
+    return COSYB200_OK;
+  }
+  if (strcmp(name, "tc_dbg") == 0) {
+    g_tc_dbg = value;   // experiment bits of the TMA variant (kernels_tc_tma.cuh)
     return COSYB200_OK;
   }
   if (strcmp(name, "tc_groups") == 0) {

@@ -144,7 +144,9 @@ int cosyb200_refine_n(cosyb200_handle* h, int slot, int B, int n_iter, const flo
  *   "dw_impl":   1 (default) shared-memory tiled depthwise + split squeeze-excite for the blocks with
  *                output <= 30x40, 0 = rolling-window depthwise + k_se_gate everywhere;
  *   "tc_groups": 0 (default) picks the tensor-core kernel variant per layer, 1 / 2 force one / two
- *                producer warpgroups (process-wide). */
+ *                producer warpgroups (process-wide);
+ *   "tc_tma":    0 (default) raw A stages of the tensor-core kernel by cp.async, 1 = EXPERIMENTAL TMA-fed stages
+ *                (faster, not yet bit-reproducible: DESIGN.md section 8; "tc_dbg" sets its experiment bits). */
 int cosyb200_set_option(cosyb200_handle* h, const char* name, int value);
 
 /* One 1x1 convolution on caller data, for kernel-level tests (reference: the Conv2d 1x1 + folded

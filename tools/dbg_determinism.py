@@ -1,5 +1,11 @@
 """Debug aid: repeats the trunk forward at the benchmark batch and reports which internal tensor of a block
-(expanded activation, depthwise output, gate, block output) is not bit-identical between repeats."""
+(expanded activation, depthwise output, gate, block output) is not bit-identical between repeats.
+
+    python tools/dbg_determinism.py                       # shipped kernels: tc_groups 1, 1, auto, auto
+    OPTS="tc_tma=1;tc_tma=1,tc_dbg=4;tc_tma=1,tc_dbg=1" REPS=12 BLK=3 python tools/dbg_determinism.py
+                                                          # the experimental TMA variant and its experiment bits
+                                                          # (kernels_tc_tma.cuh), one engine per ';'-separated set
+"""
 import os
 import sys
 from pathlib import Path
@@ -17,7 +23,11 @@ gen = torch.Generator().manual_seed(0)
 crops = torch.rand((B, 3, 240, 320), generator=gen).to(dev)
 renders = torch.rand((B, 3, 240, 320), generator=gen).to(dev)
 print('lib', os.environ.get('COSYB200_LIB'))
-for opts in ({'tc_groups': 1}, {'tc_groups': 1}, {}, {}):
+OPT_SETS = ({'tc_groups': 1}, {'tc_groups': 1}, {}, {})
+if os.environ.get('OPTS'):
+    OPT_SETS = tuple({kv.split('=')[0]: int(kv.split('=')[1]) for kv in part.split(',') if kv}
+                     for part in os.environ['OPTS'].split(';'))
+for opts in OPT_SETS:
     eng = Engine(0, max_batch=B)
     eng.load_pose_model(0, state_dict(0))
     for k, v in opts.items():
@@ -40,5 +50,6 @@ for opts in ({'tc_groups': 1}, {'tc_groups': 1}, {}, {}):
                 msg.append(f'{k}: {int(ne.sum())} elems, {rows.numel()} rows, first rows {rows[:6].tolist()} last {rows[-3:].tolist()}')
         if msg or rep == int(os.environ.get('REPS', 4)) - 1:
             print(opts, 'rep', rep, msg if msg else 'all identical')
-    eng.set_option('tc_groups', 0)
+    for k in opts:
+        eng.set_option(k, 0)          # the GEMM options are process-wide
     eng.close()
