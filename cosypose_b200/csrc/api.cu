@@ -12,7 +12,7 @@
 #include "kernels_ransac.cuh"
 #include "kernels_ba.cuh"
 #include "kernels_tc.cuh"
-#include "kernels_tc_tma.cuh"
+#include "kernels_pw2.cuh"
 #include "kernels_dwtile.cuh"
 
 namespace cosyb {
@@ -68,6 +68,20 @@ static int upload(PoseModel& m, float** dst, const std::vector<float>& v) {
   return 0;
 }
 
+// fp16 hi/lo image of a [N][K] weight for kernels_pw2.cuh
+static int upload_p2(PoseModel& m, void** dst, float* inv_scale, const float* W_nk, int N, int K) {
+  const float sc = pw2::weight_scale(W_nk, (size_t)N * K);
+  const std::vector<uint16_t> img = pw2::pack_weights(W_nk, N, K, sc);
+  void* p = nullptr;
+  int rc = dev_alloc(&p, img.size() * 2);
+  if (rc) return rc;
+  m.allocs.push_back(p);
+  CB_CUDA(cudaMemcpy(p, img.data(), img.size() * 2, cudaMemcpyHostToDevice));
+  *dst = p;
+  *inv_scale = 1.0f / sc;
+  return 0;
+}
+
 static void free_model(PoseModel& m) {
   for (void* p : m.allocs) cudaFree(p);
   m = PoseModel();
@@ -105,28 +119,15 @@ static void launch_gemm(bool gate, bool swish, bool resid, const float* A, const
 }
 
 // tensor-core path: Wpk = tc::pack_weights image of the [N][K] weight
-static int g_tc_groups = 0;   // 0: pick per layer, 1 / 2: force the producer-group variant (set_option "tc_groups")
 // No more tiles than SMs: one bigger CTA per SM with two producer groups (measured at 140 tiles: 52 vs 65 us; at
 // 210 tiles the 296 two-per-SM slots finish in one round and win, 73 vs 86 us).
 static int tc_groups_for(int tiles) { return tiles <= 148 ? 2 : 1; }
 template <int BN_MAX, bool G, bool S, bool R, int NG>
-static int launch_gemm_tc_inst(const float* A, const float* Wpk, const float* bias, const float* g,
+static int launch_gemm_tc_inst(cosyb200_handle* h, const float* A, const float* Wpk, const float* bias, const float* g,
                                const float* r, float* C, int M, int N, int K, int rows_per_img, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    CB_CUDA(cudaFuncSetAttribute(tc::k_pw_gemm_tc<BN_MAX, G, S, R, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 NG == 1 ? 112 * 1024 : 202 * 1024));
-    attr_set = true;
-  }
-  static int n_sms = 0;
-  if (n_sms == 0) {
-    int dev = 0;
-    CB_CUDA(cudaGetDevice(&dev));
-    CB_CUDA(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
   const tc::Plan p = tc::make_plan(N, K, NG);
   const int m_tiles = (M + tc::BM - 1) / tc::BM;
-  const int slots = NG == 1 ? 2 * n_sms : n_sms;
+  const int slots = NG == 1 ? 2 * h->n_sms : h->n_sms;
   const int grid = std::min(m_tiles, std::max(1, slots / p.n_tiles)) * p.n_tiles;   // multiple of n_tiles
   tc::k_pw_gemm_tc<BN_MAX, G, S, R, NG><<<grid, tc::threads_for(NG), p.smem_bytes, st>>>(
       A, Wpk, bias, g, r, C, M, N, K, rows_per_img, p.bn, p.n_tiles, p.nb, p.resident);
@@ -134,48 +135,14 @@ static int launch_gemm_tc_inst(const float* A, const float* Wpk, const float* bi
   return 0;
 }
 
-// EXPERIMENTAL opt-in variant with TMA-fed A stages (kernels_tc_tma.cuh; set_option "tc_tma" / "tc_dbg")
-static int g_tc_tma = 0, g_tc_dbg = 0;
-template <int BN_MAX, bool G, bool S, bool R, int NG>
-static int launch_gemm_tc_tma_inst(const float* A, const float* Wpk, const float* bias, const float* g,
-                                   const float* r, float* C, int M, int N, int K, int rows_per_img, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    CB_CUDA(cudaFuncSetAttribute(tc::k_pw_gemm_tc_tma<BN_MAX, G, S, R, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 NG == 1 ? 112 * 1024 : 202 * 1024));
-    attr_set = true;
-  }
-  static int n_sms = 0;
-  if (n_sms == 0) {
-    int dev = 0;
-    CB_CUDA(cudaGetDevice(&dev));
-    CB_CUDA(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
-  const tc::Plan p = tc::make_plan_tma(N, K, NG);
-  const int m_tiles = (M + tc::BM - 1) / tc::BM;
-  const int slots = NG == 1 ? 2 * n_sms : n_sms;
-  const int grid = std::min(m_tiles, std::max(1, slots / p.n_tiles)) * p.n_tiles;
-  CUtensorMap tmA;
-  if (!tc::make_a_tensor_map(&tmA, A, M, K)) {
-    set_error("launch_gemm_tc_tma: cuTensorMapEncodeTiled failed (A=%p M=%d K=%d)", (const void*)A, M, K);
-    return COSYB200_ECUDA;
-  }
-  tc::k_pw_gemm_tc_tma<BN_MAX, G, S, R, NG><<<grid, tc::threads_for(NG), p.smem_bytes, st>>>(
-      tmA, A, Wpk, bias, g, r, C, M, N, K, rows_per_img, p.bn, p.n_tiles, p.nb, p.resident, g_tc_dbg);
-  CB_LAUNCH_CHECK();
-  return 0;
-}
-
-static int launch_gemm_tc(bool gate, bool swish, bool resid, const float* A, const float* Wpk, const float* bias,
-                          const float* g, const float* r, float* C, int M, int N, int K, int rows_per_img,
-                          cudaStream_t st) {
+static int launch_gemm_tc(cosyb200_handle* h, bool gate, bool swish, bool resid, const float* A, const float* Wpk,
+                          const float* bias, const float* g, const float* r, float* C, int M, int N, int K,
+                          int rows_per_img, cudaStream_t st) {
   const tc::Plan p1 = tc::make_plan(N, K, 1);
   const int tiles = ((M + tc::BM - 1) / tc::BM) * p1.n_tiles;
-  const int ng = g_tc_groups ? g_tc_groups : tc_groups_for(tiles);
-#define TC_ARGS A, Wpk, bias, g, r, C, M, N, K, rows_per_img, st
-#define TC_DISPATCH(G, S, R)                                                                                      \
-  (g_tc_tma ? (ng == 2 ? launch_gemm_tc_tma_inst<64, G, S, R, 2>(TC_ARGS) : launch_gemm_tc_tma_inst<64, G, S, R, 1>(TC_ARGS)) \
-            : (ng == 2 ? launch_gemm_tc_inst<64, G, S, R, 2>(TC_ARGS) : launch_gemm_tc_inst<64, G, S, R, 1>(TC_ARGS)))
+  const int ng = h->tc_groups ? h->tc_groups : tc_groups_for(tiles);
+#define TC_ARGS h, A, Wpk, bias, g, r, C, M, N, K, rows_per_img, st
+#define TC_DISPATCH(G, S, R) (ng == 2 ? launch_gemm_tc_inst<64, G, S, R, 2>(TC_ARGS) : launch_gemm_tc_inst<64, G, S, R, 1>(TC_ARGS))
   if (!gate && swish && !resid) return TC_DISPATCH(false, true, false);
   if (gate && !swish && !resid) return TC_DISPATCH(true, false, false);
   if (gate && !swish && resid) return TC_DISPATCH(true, false, true);
@@ -184,6 +151,57 @@ static int launch_gemm_tc(bool gate, bool swish, bool resid, const float* A, con
 #undef TC_ARGS
   set_error("launch_gemm_tc: unsupported epilogue");
   return COSYB200_EINVAL;
+}
+
+// 3xFP16 tensor-core path (kernels_pw2.cuh): Wp2 = pw2::pack_weights image, inv_wscale = 1 / its power-of-two scale
+static int launch_pw2(cosyb200_handle* h, bool gate, bool swish, bool resid, const float* A, const void* Wp2,
+                      float inv_wscale, const float* bias, const float* g, const float* r, float* C, int M, int N,
+                      int K, int rows_per_img, cudaStream_t st) {
+  const pw2::Plan p = pw2::make_plan(M, N, K, h->n_sms);
+  if (p.bn == 0) { set_error("launch_pw2: no plan for M=%d N=%d K=%d", M, N, K); return COSYB200_EINVAL; }
+  const int gate_smem = rows_per_img >= 64 ? 1 : 0;
+#define PW2_LAUNCH_S(G, S, R, SM)                                                                                  \
+  pw2::k_pw2<G, S, R, SM><<<p.grid, pw2::THREADS, p.smem_bytes, st>>>(                                             \
+      A, (const __half*)Wp2, bias, g, r, C, M, N, K, rows_per_img, p.bn, p.n_tiles, p.nb, p.resident,             \
+      pw2::n_alloc_for(N), inv_wscale, gate_smem)
+#define PW2_LAUNCH(G, S, R) do { if (p.small) PW2_LAUNCH_S(G, S, R, true); else PW2_LAUNCH_S(G, S, R, false); } while (0)
+  if (!gate && swish && !resid) PW2_LAUNCH(false, true, false);
+  else if (gate && !swish && !resid) PW2_LAUNCH(true, false, false);
+  else if (gate && !swish && resid) PW2_LAUNCH(true, false, true);
+  else if (!gate && !swish && !resid) PW2_LAUNCH(false, false, false);
+  else { set_error("launch_pw2: unsupported epilogue"); return COSYB200_EINVAL; }
+#undef PW2_LAUNCH_S
+#undef PW2_LAUNCH
+  CB_LAUNCH_CHECK();
+  return 0;
+}
+
+// One 1x1 convolution of the trunk through the implementation selected by the handle.
+struct PwWeights { const float* kn; const float* tc; const void* p2; float p2_inv; const float* bias; };
+static int pointwise(cosyb200_handle* h, bool gate, bool swish, bool resid, const float* A, const PwWeights& w,
+                     const float* g, const float* r, float* C, int M, int N, int K, int rows_per_img, cudaStream_t st) {
+  if (h->gemm_impl == 2) return launch_pw2(h, gate, swish, resid, A, w.p2, w.p2_inv, w.bias, g, r, C, M, N, K, rows_per_img, st);
+  if (h->gemm_impl == 1) return launch_gemm_tc(h, gate, swish, resid, A, w.tc, w.bias, g, r, C, M, N, K, rows_per_img, st);
+  launch_gemm(gate, swish, resid, A, w.kn, w.bias, g, r, C, M, N, K, rows_per_img, st);
+  CB_LAUNCH_CHECK();
+  return 0;
+}
+
+// Dynamic shared memory opt-ins are per device and per function: set for every kernel that needs more than
+// 48 KB whenever a handle is created on a device (cosyb200_create, under its DeviceGuard).
+template <typename F>
+static int opt_in_smem(F* fn, int bytes) {
+  CB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  return 0;
+}
+template <bool G, bool S, bool R>
+static int opt_in_gemm_kernels() {
+  int rc = 0;
+  rc |= opt_in_smem(tc::k_pw_gemm_tc<64, G, S, R, 1>, 112 * 1024);
+  rc |= opt_in_smem(tc::k_pw_gemm_tc<64, G, S, R, 2>, 202 * 1024);
+  rc |= opt_in_smem(pw2::k_pw2<G, S, R, false>, 224 * 1024);
+  rc |= opt_in_smem(pw2::k_pw2<G, S, R, true>, 224 * 1024);
+  return rc;
 }
 
 // ---- depthwise dispatch ---------------------------------------------------------------------
@@ -224,11 +242,6 @@ static int launch_dw(const BlockSpec& b, const BlockWeights& w, const float* in,
 template <int KS, int S, int WO, int XU>
 static int launch_dw_tile_inst(const DwTilePlan& p, const BlockSpec& b, const BlockWeights& w, const float* in, float* out,
                                cosyb200_handle* h, int B, cudaStream_t st) {
-  static int smem_set = 0;
-  if (p.smem_bytes > smem_set) {
-    CB_CUDA(cudaFuncSetAttribute(k_dw_tile<KS, S, WO, XU>, cudaFuncAttributeMaxDynamicSharedMemorySize, p.smem_bytes));
-    smem_set = p.smem_bytes;
-  }
   dim3 grid(p.n_chunks, p.n_strips * p.n_xt, B);
   k_dw_tile<KS, S, WO, XU><<<grid, DWT_THREADS, p.smem_bytes, st>>>(
       in, w.dw_w, w.dw_bias, out, h->pool_partial, b.hin, b.win, b.cexp, b.hout, b.wout, b.pad_lo, p.R, p.n_xt, b.cse,
@@ -281,13 +294,8 @@ static int net_forward(cosyb200_handle* h, int slot, int B, const float* crops, 
     const float* dw_in = x;
     if (b.e != 1) {
       LaunchScope ls(h, CAT_EXPAND, st);
-      if (h->gemm_impl == 1) {
-        if (int rc2 = launch_gemm_tc(false, true, false, x, w.expand_tc, w.expand_bias, nullptr, nullptr, h->buf_e,
-                                     Min, b.cexp, b.cin, 1, st)) return rc2;
-      } else
-      launch_gemm(false, true, false, x, w.expand_kn, w.expand_bias, nullptr, nullptr, h->buf_e, Min,
-                  b.cexp, b.cin, 1, st);
-      CB_LAUNCH_CHECK();
+      const PwWeights pw{w.expand_kn, w.expand_tc, w.expand_p2, w.expand_p2_inv, w.expand_bias};
+      if (int rc2 = pointwise(h, false, true, false, x, pw, nullptr, nullptr, h->buf_e, Min, b.cexp, b.cin, 1, st)) return rc2;
       dw_in = h->buf_e;
       if ((int)i == h->dump_block && h->dump_e)
         CB_CUDA(cudaMemcpyAsync(h->dump_e, h->buf_e, (size_t)Min * b.cexp * 4, cudaMemcpyDeviceToDevice, st));
@@ -308,11 +316,6 @@ static int net_forward(cosyb200_handle* h, int slot, int B, const float* crops, 
                                            1.0f / float(b.hout * b.wout), w.se_r_b, w.se_e_w, w.se_e_b, h->gate);
     } else {
       LaunchScope ls(h, CAT_SE, st);
-      static bool se_attr = false;
-      if (!se_attr) {
-        CB_CUDA(cudaFuncSetAttribute(k_se_gate, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        se_attr = true;
-      }
       const dim3 se_grid((B + SE_IMGS - 1) / SE_IMGS, b.cexp >= 1024 ? 8 : (b.cexp >= 256 ? 4 : 1));
       const size_t se_smem = (size_t)SE_IMGS * (b.cexp + b.cse) * sizeof(float);
       k_se_gate<<<se_grid, SE_THREADS, se_smem, st>>>(B, h->pool_partial, p.tiles, b.cexp, b.cse,
@@ -326,14 +329,10 @@ static int net_forward(cosyb200_handle* h, int slot, int B, const float* crops, 
     }
     {
       LaunchScope ls(h, CAT_PROJECT, st);
-      if (h->gemm_impl == 1) {
-        if (int rc2 = launch_gemm_tc(true, false, b.skip != 0, h->buf_d, w.proj_tc, w.proj_bias, h->gate, x, y, Mout,
-                                     b.cout, b.cexp, b.hout * b.wout, st)) return rc2;
-      } else
-      launch_gemm(true, false, b.skip != 0, h->buf_d, w.proj_kn, w.proj_bias, h->gate, x, y, Mout, b.cout,
-                  b.cexp, b.hout * b.wout, st);
+      const PwWeights pw{w.proj_kn, w.proj_tc, w.proj_p2, w.proj_p2_inv, w.proj_bias};
+      if (int rc2 = pointwise(h, true, false, b.skip != 0, h->buf_d, pw, h->gate, x, y, Mout, b.cout, b.cexp,
+                              b.hout * b.wout, st)) return rc2;
     }
-    CB_LAUNCH_CHECK();
     cur ^= 1;
     rc = tap(1 + (int)i, y, (size_t)Mout * b.cout);
     if (rc) return rc;
@@ -343,14 +342,10 @@ static int net_forward(cosyb200_handle* h, int slot, int B, const float* crops, 
   const int n_pos = last.hout * last.wout;
   {
     LaunchScope ls(h, CAT_HEAD, st);
-    if (h->gemm_impl == 1) {
-      if (int rc2 = launch_gemm_tc(false, true, false, h->act[cur], m.head_tc, m.head_bias, nullptr, nullptr, h->buf_e,
-                                   B * n_pos, N_FEATURES, last.cout, 1, st)) return rc2;
-    } else
-    launch_gemm(false, true, false, h->act[cur], m.head_kn, m.head_bias, nullptr, nullptr, h->buf_e,
-                B * n_pos, N_FEATURES, last.cout, 1, st);
+    const PwWeights pw{m.head_kn, m.head_tc, m.head_p2, m.head_p2_inv, m.head_bias};
+    if (int rc2 = pointwise(h, false, true, false, h->act[cur], pw, nullptr, nullptr, h->buf_e, B * n_pos, N_FEATURES,
+                            last.cout, 1, st)) return rc2;
   }
-  CB_LAUNCH_CHECK();
   rc = tap(1 + (int)h->blocks.size(), h->buf_e, (size_t)B * n_pos * N_FEATURES);
   if (rc) return rc;
   {
@@ -422,6 +417,24 @@ int cosyb200_create(cosyb200_handle** out, int device, int max_batch) {
   CB_CUDA(cudaGetDeviceProperties(&prop, device));
   CB_CHECK_ARG(prop.major == 10, "create: device %d is sm_%d%d; this engine is built for sm_100a only",
                device, prop.major, prop.minor);
+  {
+    // per-device, per-function opt-ins (idempotent; repeated for every handle so that each device gets them)
+    int rc = 0;
+    rc |= opt_in_gemm_kernels<false, true, false>();
+    rc |= opt_in_gemm_kernels<true, false, false>();
+    rc |= opt_in_gemm_kernels<true, false, true>();
+    rc |= opt_in_gemm_kernels<false, false, false>();
+    rc |= opt_in_smem(k_roi_crop, (int)(CROP_SMEM_FLOATS * sizeof(float)));
+    rc |= opt_in_smem(k_se_gate, 100 * 1024);
+    rc |= opt_in_smem(k_dw_tile<5, 1, 40, 1>, 80 * 1024);
+    rc |= opt_in_smem(k_dw_tile<3, 2, 20, 1>, 80 * 1024);
+    rc |= opt_in_smem(k_dw_tile<3, 1, 20, 1>, 80 * 1024);
+    rc |= opt_in_smem(k_dw_tile<5, 1, 20, 1>, 80 * 1024);
+    rc |= opt_in_smem(k_dw_tile<5, 2, 10, 1>, 80 * 1024);
+    rc |= opt_in_smem(k_dw_tile<5, 1, 10, 1>, 80 * 1024);
+    rc |= opt_in_smem(k_dw_tile<3, 1, 10, 1>, 80 * 1024);
+    if (rc) return COSYB200_ECUDA;
+  }
   cosyb200_handle* h = new cosyb200_handle();
   h->device = device;
   h->max_batch = max_batch;
@@ -543,6 +556,7 @@ int cosyb200_load_pose_model(cosyb200_handle* h, int slot, int n, const char* co
       rc |= upload(m, &w.expand_nk, nk);
       rc |= upload(m, &w.expand_kn, kn);
       rc |= upload(m, &w.expand_tc, tc::pack_weights(nk.data(), b.cexp, b.cin));
+      rc |= upload_p2(m, &w.expand_p2, &w.expand_p2_inv, nk.data(), b.cexp, b.cin);
       rc |= upload(m, &w.expand_bias, shift);
     }
     {
@@ -582,6 +596,7 @@ int cosyb200_load_pose_model(cosyb200_handle* h, int slot, int n, const char* co
       rc |= upload(m, &w.proj_nk, nk);
       rc |= upload(m, &w.proj_kn, kn);
       rc |= upload(m, &w.proj_tc, tc::pack_weights(nk.data(), b.cout, b.cexp));
+      rc |= upload_p2(m, &w.proj_p2, &w.proj_p2_inv, nk.data(), b.cout, b.cexp);
       rc |= upload(m, &w.proj_bias, shift);
     }
   }
@@ -593,6 +608,7 @@ int cosyb200_load_pose_model(cosyb200_handle* h, int slot, int n, const char* co
     rc |= upload(m, &m.head_nk, nk);
     rc |= upload(m, &m.head_kn, kn);
     rc |= upload(m, &m.head_tc, tc::pack_weights(nk.data(), N_FEATURES, cin));
+    rc |= upload_p2(m, &m.head_p2, &m.head_p2_inv, nk.data(), N_FEATURES, cin);
     rc |= upload(m, &m.head_bias, shift);
     const float* fw = get("pose_fc.weight", (int64_t)POSE_DIM * N_FEATURES);
     const float* fb = get("pose_fc.bias", POSE_DIM);
@@ -623,8 +639,13 @@ int cosyb200_set_meshes(cosyb200_handle* h, int n_labels, int n_points, const fl
   CB_CHECK_ARG((points == nullptr) || (n_sample == N_SAMPLE && point_ids && n_points >= n_sample),
                "set_meshes: need %d sampled point ids out of >= %d points", N_SAMPLE, N_SAMPLE);
   DeviceGuard guard(h->device);
-  for (void* p : {(void*)h->pts_sampled, (void*)h->sym, (void*)h->n_sym, (void*)h->aabb}) if (p) cudaFree(p);
-  h->pts_sampled = nullptr; h->sym = nullptr; h->n_sym = nullptr; h->aabb = nullptr;
+  // points == NULL replaces the symmetry / AABB tables only: an engine shared with the pose predictors keeps
+  // its sampled points (they belong to the same label set)
+  CB_CHECK_ARG(points != nullptr || h->pts_sampled == nullptr || n_labels == h->n_labels,
+               "set_meshes: %d labels without points on an engine holding points of %d labels", n_labels, h->n_labels);
+  if (points && h->pts_sampled) { cudaFree(h->pts_sampled); h->pts_sampled = nullptr; }
+  for (void* p : {(void*)h->sym, (void*)h->n_sym, (void*)h->aabb}) if (p) cudaFree(p);
+  h->sym = nullptr; h->n_sym = nullptr; h->aabb = nullptr;
   h->n_labels = n_labels;
   h->s_max = s_max;
   for (int l = 0; l < n_labels; ++l)
@@ -679,12 +700,7 @@ int cosyb200_prepare_iter(cosyb200_handle* h, int B, int img_h, int img_w, const
 
 static int launch_crop(cosyb200_handle* h, int B, const float* images, int n_images, int img_h, int img_w,
                        const int32_t* im_ids, const float* boxes_crop, float* crops, cudaStream_t st) {
-  static bool attr_set = false;
   const size_t smem = CROP_SMEM_FLOATS * sizeof(float);
-  if (!attr_set) {
-    CB_CUDA(cudaFuncSetAttribute(k_roi_crop, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
   dim3 grid(RENDER_H / CROP_PH, B);
   {
     LaunchScope ls(h, CAT_CROP, st);
@@ -760,22 +776,13 @@ int cosyb200_refine_n(cosyb200_handle* h, int slot, int B, int n_iter, const flo
 int cosyb200_set_option(cosyb200_handle* h, const char* name, int value) {
   CB_CHECK_ARG(h != nullptr && name != nullptr, "set_option: bad arguments");
   if (strcmp(name, "gemm_impl") == 0) {
-    CB_CHECK_ARG(value == 0 || value == 1, "set_option: gemm_impl must be 0 (cuda cores) or 1 (tcgen05)");
+    CB_CHECK_ARG(value >= 0 && value <= 2, "set_option: gemm_impl must be 0 (cuda cores), 1 (tcgen05 3xTF32) or 2 (tcgen05 3xFP16)");
     h->gemm_impl = value;
-    return COSYB200_OK;
-  }
-  if (strcmp(name, "tc_tma") == 0) {
-    CB_CHECK_ARG(value == 0 || value == 1, "set_option: tc_tma must be 0 (cp.async A stages) or 1 (experimental TMA A stages)");
-    g_tc_tma = value;
-    return COSYB200_OK;
-  }
-  if (strcmp(name, "tc_dbg") == 0) {
-    g_tc_dbg = value;   // experiment bits of the TMA variant (kernels_tc_tma.cuh)
     return COSYB200_OK;
   }
   if (strcmp(name, "tc_groups") == 0) {
     CB_CHECK_ARG(value >= 0 && value <= 2, "set_option: tc_groups must be 0 (per layer), 1 or 2");
-    g_tc_groups = value;
+    h->tc_groups = value;
     return COSYB200_OK;
   }
   if (strcmp(name, "dw_impl") == 0) {
@@ -795,7 +802,14 @@ int cosyb200_debug_pointwise(cosyb200_handle* h, int impl, int M, int N, int K, 
   DeviceGuard guard(h->device);
   cudaStream_t st = (cudaStream_t)stream;
   std::vector<float> w;
-  if (impl == 1) {
+  float p2_inv = 1.f;
+  if (impl == 2) {
+    const float sc = pw2::weight_scale(W_nk_host, (size_t)N * K);
+    const std::vector<uint16_t> img = pw2::pack_weights(W_nk_host, N, K, sc);
+    w.resize((img.size() + 1) / 2);
+    memcpy(w.data(), img.data(), img.size() * 2);
+    p2_inv = 1.0f / sc;
+  } else if (impl == 1) {
     w = tc::pack_weights(W_nk_host, N, K);
   } else {
     w.resize((size_t)N * K);
@@ -810,7 +824,9 @@ int cosyb200_debug_pointwise(cosyb200_handle* h, int impl, int M, int N, int K, 
   int rc = 0;
   {
     LaunchScope ls(h, CAT_EXPAND, st);
-    if (impl == 1) rc = launch_gemm_tc(gate != nullptr, swish != 0, resid != nullptr, A, dW, dB, gate, resid, C, M, N, K,
+    if (impl == 2) rc = launch_pw2(h, gate != nullptr, swish != 0, resid != nullptr, A, dW, p2_inv, dB, gate, resid, C, M,
+                                   N, K, rows_per_img, st);
+    else if (impl == 1) rc = launch_gemm_tc(h, gate != nullptr, swish != 0, resid != nullptr, A, dW, dB, gate, resid, C, M, N, K,
                                        rows_per_img, st);
     else launch_gemm(gate != nullptr, swish != 0, resid != nullptr, A, dW, dB, gate, resid, C, M, N, K, rows_per_img, st);
   }

@@ -63,6 +63,10 @@ struct BlockWeights {
   float* proj_bias = nullptr;   // [cout]
   float* expand_tc = nullptr;   // tensor-core image of expand_nk (kernels_tc.cuh pack_weights)
   float* proj_tc = nullptr;     // tensor-core image of proj_nk
+  void* expand_p2 = nullptr;    // fp16 hi/lo image of expand_nk (kernels_pw2.cuh pack_weights)
+  void* proj_p2 = nullptr;      // fp16 hi/lo image of proj_nk
+  float expand_p2_inv = 1.f;    // 1 / (power-of-two weight scale) of the images
+  float proj_p2_inv = 1.f;
 };
 
 struct PoseModel {
@@ -74,6 +78,8 @@ struct PoseModel {
   float* head_kn = nullptr;    // [384][1536]
   float* head_bias = nullptr;  // [1536]
   float* head_tc = nullptr;    // tensor-core image of head_nk
+  void* head_p2 = nullptr;     // fp16 hi/lo image of head_nk
+  float head_p2_inv = 1.f;
   float* fc_w = nullptr;       // [9][1536]
   float* fc_b = nullptr;       // [9]
   std::vector<void*> allocs;
@@ -111,11 +117,12 @@ struct cosyb200_handle {
   int cur_block = N_BLK - 1;
   std::vector<int> ev_blk;
   bool profiling = false;
+  int tc_groups = 0;   // 3xTF32 kernel: 0 = pick the producer-group variant per layer, 1 / 2 = force it
   int dw_impl = 1;     // depthwise of the small-spatial blocks: 0 = rolling window + k_se_gate, 1 = k_dw_tile + k_se_fc2
   // debugging aid (cosyb200_debug_dump): copies of block `dump_block`'s internal tensors
   int dump_block = -1;
   float* dump_e = nullptr; float* dump_d = nullptr; float* dump_gate = nullptr;
-  int gemm_impl = 1;   // 1x1 convolutions: 0 = CUDA-core fp32 kernel, 1 = tcgen05 3xTF32 kernel
+  int gemm_impl = 2;   // 1x1 convolutions: 0 = CUDA-core fp32 kernel, 1 = tcgen05 3xTF32 kernel, 2 = tcgen05 3xFP16 kernel (kernels_pw2.cuh)
   std::vector<cudaEvent_t> ev_pool;   // pairs: [2*i] start, [2*i+1] stop
   std::vector<int> ev_cat;            // category of each recorded pair
   cudaStream_t ev_stream = nullptr;

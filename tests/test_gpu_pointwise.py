@@ -1,4 +1,4 @@
-"""Kernel-level parity of the 1x1 convolution kernels (tcgen05 3xTF32 and CUDA-core fp32) against a
+"""Kernel-level parity of the 1x1 convolution kernels (tcgen05 3xFP16 / 3xTF32 and CUDA-core fp32) against a
 float64 torch reference, on every (K, N) pair the EfficientNet-B3 trunk uses plus ragged M."""
 import numpy as np
 import pytest
@@ -36,7 +36,7 @@ def _ref(A, W, bias, gate, rows, resid, swish):
     return y
 
 
-@pytest.mark.parametrize('impl,groups', [(1, 1), (1, 2), (0, 0)])
+@pytest.mark.parametrize('impl,groups', [(2, 0), (1, 1), (1, 2), (0, 0)])
 def test_all_trunk_shapes(eng, impl, groups):
     """groups: producer-warpgroup variant of the tensor-core kernel (1: two CTAs per SM, 2: one CTA per SM)."""
     dev = eng.device
@@ -62,9 +62,9 @@ def test_all_trunk_shapes(eng, impl, groups):
     print('worst relative error', worst)
 
 
-@pytest.mark.parametrize('groups', [1, 2])
+@pytest.mark.parametrize('impl,groups', [(2, 0), (1, 1), (1, 2)])
 @pytest.mark.parametrize('M', [1, 127, 128, 129, 4480, 19200 * 2 + 5])
-def test_row_counts(eng, M, groups):
+def test_row_counts(eng, M, impl, groups):
     dev = eng.device
     eng.set_option('tc_groups', groups)
     gen = torch.Generator().manual_seed(M)
@@ -72,17 +72,17 @@ def test_row_counts(eng, M, groups):
     A = torch.randn((M, K), generator=gen)
     W = torch.randn((N, K), generator=gen) / np.sqrt(K)
     bias = torch.randn(N, generator=gen)
-    out = eng.debug_pointwise(1, A.to(dev), W, bias, swish=True)
+    out = eng.debug_pointwise(impl, A.to(dev), W, bias, swish=True)
     ref = _ref(A, W, bias, None, 1, None, True)
     eng.set_option('tc_groups', 0)
     assert (out.cpu().double() - ref).abs().max().item() < 2e-6 * ref.abs().max().item()
 
 
-@pytest.mark.parametrize('groups', [1, 2])
+@pytest.mark.parametrize('impl,groups', [(2, 0), (1, 1), (1, 2)])
 @pytest.mark.parametrize('M,K,N,kind', [(19200, 816, 136, 'project'), (4480, 1392, 232, 'project'),
                                         (4480, 232, 1392, 'expand'), (76800, 192, 32, 'project'),
                                         (19200, 96, 576, 'expand')])
-def test_repeatable(eng, M, K, N, kind, groups):
+def test_repeatable(eng, M, K, N, kind, impl, groups):
     """Bit-identical results over repeated launches at the benchmark sizes (every barrier hand-off in the
     pipelined kernel is exercised thousands of times per launch: a missing dependency shows up here)."""
     dev = eng.device
@@ -94,11 +94,11 @@ def test_repeatable(eng, M, K, N, kind, groups):
     bias = torch.randn(N, generator=gen)
     gate = torch.rand((-(-M // rows), K), generator=gen).to(dev) if kind == 'project' else None
     resid = torch.randn((M, N), generator=gen).to(dev) if kind == 'project' and K == 6 * N else None
-    first = eng.debug_pointwise(1, A, W, bias, gate, rows, resid, kind != 'project').clone()
+    first = eng.debug_pointwise(impl, A, W, bias, gate, rows, resid, kind != 'project').clone()
     ref = _ref(A.cpu(), W, bias, gate.cpu() if gate is not None else None, rows,
                resid.cpu() if resid is not None else None, kind != 'project')
     assert (first.cpu().double() - ref).abs().max().item() < 2e-6 * ref.abs().max().item()
     for _ in range(8):
-        again = eng.debug_pointwise(1, A, W, bias, gate, rows, resid, kind != 'project')
+        again = eng.debug_pointwise(impl, A, W, bias, gate, rows, resid, kind != 'project')
         assert torch.equal(first, again)
     eng.set_option('tc_groups', 0)

@@ -4,7 +4,7 @@ from helpers import Workload, build_predictor
 from cosypose_b200.utils import tensor_collection as tc
 dev=torch.device('cuda',0)
 g=np.load('/root/repo/tests/golden/single_view_zup.npz')
-for impl in (0,1):
+for impl in (0,1,2):
     w=Workload(1,2,3,1,1)
     pred,eng,views=build_predictor(w,0)
     eng.set_option('gemm_impl',impl)
