@@ -13,6 +13,7 @@
 #include "kernels_ba.cuh"
 #include "kernels_tc.cuh"
 #include "kernels_pw2.cuh"
+#include "kernels_xdw.cuh"
 #include "kernels_dwtile.cuh"
 
 namespace cosyb {
@@ -80,6 +81,22 @@ static int upload_p2(PoseModel& m, void** dst, float* inv_scale, const float* W_
   *dst = p;
   *inv_scale = 1.0f / sc;
   return 0;
+}
+
+// fp16 hi/lo chunk images of an expand weight plus its zero-padded bias for kernels_xdw.cuh
+static int upload_xdw(PoseModel& m, BlockWeights& w, const float* W_nk, const std::vector<float>& bias, int N, int K) {
+  const float sc = pw2::weight_scale(W_nk, (size_t)N * K);
+  const std::vector<uint16_t> img = xdw::pack_weights(W_nk, N, K, sc);
+  void* p = nullptr;
+  int rc = dev_alloc(&p, img.size() * 2);
+  if (rc) return rc;
+  m.allocs.push_back(p);
+  CB_CUDA(cudaMemcpy(p, img.data(), img.size() * 2, cudaMemcpyHostToDevice));
+  w.expand_x = p;
+  w.expand_x_inv = 1.0f / sc;
+  std::vector<float> bp((size_t)xdw::n_chunks_for(N) * xdw::CC, 0.f);
+  for (int i = 0; i < N; ++i) bp[i] = bias[i];
+  return upload(m, &w.expand_x_bias, bp);
 }
 
 static void free_model(PoseModel& m) {
@@ -265,6 +282,31 @@ static bool use_dw_tile(const cosyb200_handle* h, const BlockSpec& b) {
   return h->dw_impl != 0 && dw_tile_plan(b).ok;
 }
 
+// fused expand + depthwise + pooling (kernels_xdw.cuh)
+static bool use_xdw(const cosyb200_handle* h, const BlockSpec& b) { return h->xdw != 0 && xdw::make_plan(b).ok; }
+
+template <int KS, int S, int NX>
+static int launch_xdw_inst(const xdw::Plan& p, cosyb200_handle* h, const BlockSpec& b, const BlockWeights& w,
+                           const float* x, float* out, int B, cudaStream_t st) {
+  const int n_items = B * p.tiles_y * p.tiles_x;
+  xdw::k_xdw<KS, S, NX><<<std::min(n_items, h->n_sms), xdw::THREADS, p.smem_bytes, st>>>(
+      x, (const __half*)w.expand_x, w.expand_x_bias, w.expand_x_inv, w.dw_w, w.dw_bias, out, h->pool_partial, B, b.hin,
+      b.win, b.cin, b.cexp, b.hout, b.wout, b.pad_lo, p.MT, p.TH, p.TW, p.IH, p.IW, p.tiles_y, p.tiles_x, p.n_chunks,
+      p.Kp, p.NYS);
+  CB_LAUNCH_CHECK();
+  return 0;
+}
+
+static int launch_xdw(cosyb200_handle* h, const BlockSpec& b, const BlockWeights& w, const float* x, float* out, int B,
+                      cudaStream_t st) {
+  const xdw::Plan p = xdw::make_plan(b);
+#define XDW(KS, S, NXV) if (b.k == KS && b.s == S && p.NX == NXV) return launch_xdw_inst<KS, S, NXV>(p, h, b, w, x, out, B, st)
+  XDW(3, 2, 2); XDW(3, 1, 4); XDW(5, 2, 2); XDW(5, 1, 4);
+#undef XDW
+  set_error("launch_xdw: no instance for k=%d s=%d NX=%d", b.k, b.s, p.NX);
+  return COSYB200_EINVAL;
+}
+
 // ---- trunk forward --------------------------------------------------------------------------
 static int net_forward(cosyb200_handle* h, int slot, int B, const float* crops, const void* renders,
                        int render_u8, float* pose9, float* const* taps, const float* TCO_in, const float* K_crop,
@@ -292,7 +334,12 @@ static int net_forward(cosyb200_handle* h, int slot, int B, const float* crops, 
     float* y = h->act[cur ^ 1];
     const int Min = B * b.hin * b.win, Mout = B * b.hout * b.wout;
     const float* dw_in = x;
-    if (b.e != 1) {
+    const bool fused = use_xdw(h, b);
+    if (fused) {
+      LaunchScope ls(h, CAT_DW, st);
+      if (int rc2 = launch_xdw(h, b, w, x, h->buf_d, B, st)) return rc2;
+    }
+    if (b.e != 1 && !fused) {
       LaunchScope ls(h, CAT_EXPAND, st);
       const PwWeights pw{w.expand_kn, w.expand_tc, w.expand_p2, w.expand_p2_inv, w.expand_bias};
       if (int rc2 = pointwise(h, false, true, false, x, pw, nullptr, nullptr, h->buf_e, Min, b.cexp, b.cin, 1, st)) return rc2;
@@ -300,14 +347,18 @@ static int net_forward(cosyb200_handle* h, int slot, int B, const float* crops, 
       if ((int)i == h->dump_block && h->dump_e)
         CB_CUDA(cudaMemcpyAsync(h->dump_e, h->buf_e, (size_t)Min * b.cexp * 4, cudaMemcpyDeviceToDevice, st));
     }
-    const bool tile_dw = use_dw_tile(h, b);
-    {
+    const bool tile_dw = !fused && use_dw_tile(h, b);
+    if (!fused) {
       LaunchScope ls(h, CAT_DW, st);
       if (tile_dw) rc = launch_dw_tile(dw_tile_plan(b), b, w, dw_in, h->buf_d, h, B, st);
       else rc = launch_dw(b, w, dw_in, h->buf_d, h->pool_partial, B, st);
     }
     if (rc) return rc;
     DwPlan p = dw_plan(b);
+    if (fused) {
+      const xdw::Plan xp = xdw::make_plan(b);
+      p.tiles = xp.tiles_y * xp.tiles_x;
+    }
     if (tile_dw) {
       const DwTilePlan tp = dw_tile_plan(b);
       LaunchScope ls(h, CAT_SE, st);
@@ -424,6 +475,10 @@ int cosyb200_create(cosyb200_handle** out, int device, int max_batch) {
     rc |= opt_in_gemm_kernels<true, false, false>();
     rc |= opt_in_gemm_kernels<true, false, true>();
     rc |= opt_in_gemm_kernels<false, false, false>();
+    rc |= opt_in_smem(xdw::k_xdw<3, 2, 2>, 200 * 1024);
+    rc |= opt_in_smem(xdw::k_xdw<3, 1, 4>, 200 * 1024);
+    rc |= opt_in_smem(xdw::k_xdw<5, 2, 2>, 200 * 1024);
+    rc |= opt_in_smem(xdw::k_xdw<5, 1, 4>, 200 * 1024);
     rc |= opt_in_smem(k_roi_crop, (int)(CROP_SMEM_FLOATS * sizeof(float)));
     rc |= opt_in_smem(k_se_gate, 100 * 1024);
     rc |= opt_in_smem(k_dw_tile<5, 1, 40, 1>, 80 * 1024);
@@ -446,6 +501,7 @@ int cosyb200_create(cosyb200_handle** out, int device, int max_batch) {
     if (b.e != 1) e = std::max(e, (size_t)b.hin * b.win * b.cexp);
     d = std::max(d, (size_t)b.hout * b.wout * b.cexp);
     part = std::max(part, (size_t)dw_plan(b).tiles * b.cexp);
+    if (xdw::make_plan(b).ok) part = std::max(part, (size_t)xdw::make_plan(b).tiles_y * xdw::make_plan(b).tiles_x * b.cexp);
     if (dw_tile_plan(b).ok)
       part = std::max(part, (size_t)dw_tile_plan(b).n_strips * dw_tile_plan(b).n_xt * dw_tile_plan(b).n_chunks * b.cse);
     cmax = std::max(cmax, (size_t)b.cexp);
@@ -558,6 +614,7 @@ int cosyb200_load_pose_model(cosyb200_handle* h, int slot, int n, const char* co
       rc |= upload(m, &w.expand_tc, tc::pack_weights(nk.data(), b.cexp, b.cin));
       rc |= upload_p2(m, &w.expand_p2, &w.expand_p2_inv, nk.data(), b.cexp, b.cin);
       rc |= upload(m, &w.expand_bias, shift);
+      if (xdw::make_plan(b).ok) rc |= upload_xdw(m, w, nk.data(), shift, b.cexp, b.cin);
     }
     {
       const int kk = b.k * b.k;
@@ -783,6 +840,11 @@ int cosyb200_set_option(cosyb200_handle* h, const char* name, int value) {
   if (strcmp(name, "tc_groups") == 0) {
     CB_CHECK_ARG(value >= 0 && value <= 2, "set_option: tc_groups must be 0 (per layer), 1 or 2");
     h->tc_groups = value;
+    return COSYB200_OK;
+  }
+  if (strcmp(name, "xdw") == 0) {
+    CB_CHECK_ARG(value == 0 || value == 1, "set_option: xdw must be 0 (separate expand and depthwise kernels) or 1 (fused)");
+    h->xdw = value;
     return COSYB200_OK;
   }
   if (strcmp(name, "dw_impl") == 0) {
