@@ -83,10 +83,10 @@ static int upload_p2(PoseModel& m, void** dst, float* inv_scale, const float* W_
   return 0;
 }
 
-// fp16 hi/lo chunk images of an expand weight plus its zero-padded bias for kernels_xdw.cuh
-static int upload_xdw(PoseModel& m, BlockWeights& w, const float* W_nk, const std::vector<float>& bias, int N, int K) {
-  const float sc = pw2::weight_scale(W_nk, (size_t)N * K);
-  const std::vector<uint16_t> img = xdw::pack_weights(W_nk, N, K, sc);
+// fp16 hi/lo chunk images of an expand weight (bias as an extra k row) for kernels_xdw.cuh
+static int upload_xdw(PoseModel& m, BlockWeights& w, const float* W_nk, const std::vector<float>& bias, int N, int K, int cc) {
+  const float sc = xdw::weight_scale(W_nk, bias.data(), N, K);
+  const std::vector<uint16_t> img = xdw::pack_weights(W_nk, bias.data(), N, K, cc, sc);
   void* p = nullptr;
   int rc = dev_alloc(&p, img.size() * 2);
   if (rc) return rc;
@@ -94,9 +94,7 @@ static int upload_xdw(PoseModel& m, BlockWeights& w, const float* W_nk, const st
   CB_CUDA(cudaMemcpy(p, img.data(), img.size() * 2, cudaMemcpyHostToDevice));
   w.expand_x = p;
   w.expand_x_inv = 1.0f / sc;
-  std::vector<float> bp((size_t)xdw::n_chunks_for(N) * xdw::CC, 0.f);
-  for (int i = 0; i < N; ++i) bp[i] = bias[i];
-  return upload(m, &w.expand_x_bias, bp);
+  return 0;
 }
 
 static void free_model(PoseModel& m) {
@@ -285,14 +283,14 @@ static bool use_dw_tile(const cosyb200_handle* h, const BlockSpec& b) {
 // fused expand + depthwise + pooling (kernels_xdw.cuh)
 static bool use_xdw(const cosyb200_handle* h, const BlockSpec& b) { return h->xdw != 0 && xdw::make_plan(b).ok; }
 
-template <int KS, int S, int NX>
+template <int KS, int S, int NX, int CCT>
 static int launch_xdw_inst(const xdw::Plan& p, cosyb200_handle* h, const BlockSpec& b, const BlockWeights& w,
                            const float* x, float* out, int B, cudaStream_t st) {
   const int n_items = B * p.tiles_y * p.tiles_x;
-  xdw::k_xdw<KS, S, NX><<<std::min(n_items, h->n_sms), xdw::THREADS, p.smem_bytes, st>>>(
-      x, (const __half*)w.expand_x, w.expand_x_bias, w.expand_x_inv, w.dw_w, w.dw_bias, out, h->pool_partial, B, b.hin,
-      b.win, b.cin, b.cexp, b.hout, b.wout, b.pad_lo, p.MT, p.TH, p.TW, p.IH, p.IW, p.tiles_y, p.tiles_x, p.n_chunks,
-      p.Kp, p.NYS);
+  xdw::k_xdw<KS, S, NX, CCT><<<std::min(n_items, h->n_sms), xdw::THREADS, p.smem_bytes, st>>>(
+      x, (const __half*)w.expand_x, w.expand_x_inv, w.dw_w, w.dw_bias, out, h->pool_partial, B, b.hin, b.win, b.cin,
+      b.cexp, b.hout, b.wout, b.pad_lo, p.MT, p.TH, p.TW, p.IH, p.IW, p.tiles_y, p.tiles_x, p.n_chunks, p.Kp,
+      p.NYS, h->cur_block == h->trace_block ? 1 : 0);
   CB_LAUNCH_CHECK();
   return 0;
 }
@@ -300,8 +298,8 @@ static int launch_xdw_inst(const xdw::Plan& p, cosyb200_handle* h, const BlockSp
 static int launch_xdw(cosyb200_handle* h, const BlockSpec& b, const BlockWeights& w, const float* x, float* out, int B,
                       cudaStream_t st) {
   const xdw::Plan p = xdw::make_plan(b);
-#define XDW(KS, S, NXV) if (b.k == KS && b.s == S && p.NX == NXV) return launch_xdw_inst<KS, S, NXV>(p, h, b, w, x, out, B, st)
-  XDW(3, 2, 2); XDW(3, 1, 4); XDW(5, 2, 2); XDW(5, 1, 4);
+#define XDW(KS, S, NXV, CCV) if (b.k == KS && b.s == S && p.NX == NXV && p.cc == CCV) return launch_xdw_inst<KS, S, NXV, CCV>(p, h, b, w, x, out, B, st)
+  XDW(3, 2, 1, 48); XDW(3, 1, 2, 64); XDW(5, 2, 1, 64); XDW(5, 1, 2, 48); XDW(3, 2, 2, 48);
 #undef XDW
   set_error("launch_xdw: no instance for k=%d s=%d NX=%d", b.k, b.s, p.NX);
   return COSYB200_EINVAL;
@@ -475,10 +473,11 @@ int cosyb200_create(cosyb200_handle** out, int device, int max_batch) {
     rc |= opt_in_gemm_kernels<true, false, false>();
     rc |= opt_in_gemm_kernels<true, false, true>();
     rc |= opt_in_gemm_kernels<false, false, false>();
-    rc |= opt_in_smem(xdw::k_xdw<3, 2, 2>, 200 * 1024);
-    rc |= opt_in_smem(xdw::k_xdw<3, 1, 4>, 200 * 1024);
-    rc |= opt_in_smem(xdw::k_xdw<5, 2, 2>, 200 * 1024);
-    rc |= opt_in_smem(xdw::k_xdw<5, 1, 4>, 200 * 1024);
+    rc |= opt_in_smem(xdw::k_xdw<3, 2, 1, 48>, 200 * 1024);
+    rc |= opt_in_smem(xdw::k_xdw<3, 1, 2, 64>, 200 * 1024);
+    rc |= opt_in_smem(xdw::k_xdw<5, 2, 1, 64>, 200 * 1024);
+    rc |= opt_in_smem(xdw::k_xdw<5, 1, 2, 48>, 200 * 1024);
+    rc |= opt_in_smem(xdw::k_xdw<3, 2, 2, 48>, 200 * 1024);
     rc |= opt_in_smem(k_roi_crop, (int)(CROP_SMEM_FLOATS * sizeof(float)));
     rc |= opt_in_smem(k_se_gate, 100 * 1024);
     rc |= opt_in_smem(k_dw_tile<5, 1, 40, 1>, 80 * 1024);
@@ -614,7 +613,7 @@ int cosyb200_load_pose_model(cosyb200_handle* h, int slot, int n, const char* co
       rc |= upload(m, &w.expand_tc, tc::pack_weights(nk.data(), b.cexp, b.cin));
       rc |= upload_p2(m, &w.expand_p2, &w.expand_p2_inv, nk.data(), b.cexp, b.cin);
       rc |= upload(m, &w.expand_bias, shift);
-      if (xdw::make_plan(b).ok) rc |= upload_xdw(m, w, nk.data(), shift, b.cexp, b.cin);
+      if (xdw::make_plan(b).ok) rc |= upload_xdw(m, w, nk.data(), shift, b.cexp, b.cin, xdw::make_plan(b).cc);
     }
     {
       const int kk = b.k * b.k;
@@ -845,6 +844,10 @@ int cosyb200_set_option(cosyb200_handle* h, const char* name, int value) {
   if (strcmp(name, "xdw") == 0) {
     CB_CHECK_ARG(value == 0 || value == 1, "set_option: xdw must be 0 (separate expand and depthwise kernels) or 1 (fused)");
     h->xdw = value;
+    return COSYB200_OK;
+  }
+  if (strcmp(name, "trace_block") == 0) {
+    h->trace_block = value;
     return COSYB200_OK;
   }
   if (strcmp(name, "dw_impl") == 0) {

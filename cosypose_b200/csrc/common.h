@@ -65,8 +65,7 @@ struct BlockWeights {
   float* proj_tc = nullptr;     // tensor-core image of proj_nk
   void* expand_p2 = nullptr;    // fp16 hi/lo image of expand_nk (kernels_pw2.cuh pack_weights)
   void* proj_p2 = nullptr;      // fp16 hi/lo image of proj_nk
-  void* expand_x = nullptr;     // fp16 hi/lo chunk images of expand_nk for the fused kernel (kernels_xdw.cuh pack_weights)
-  float* expand_x_bias = nullptr;  // [n_chunks * 64] zero padded
+  void* expand_x = nullptr;     // fp16 hi/lo chunk images of expand_nk + bias row for the fused kernel (kernels_xdw.cuh)
   float expand_x_inv = 1.f;
   float expand_p2_inv = 1.f;    // 1 / (power-of-two weight scale) of the images
   float proj_p2_inv = 1.f;
@@ -121,6 +120,7 @@ struct cosyb200_handle {
   std::vector<int> ev_blk;
   bool profiling = false;
   int tc_groups = 0;   // 3xTF32 kernel: 0 = pick the producer-group variant per layer, 1 / 2 = force it
+  int trace_block = -1;   // debugging: the fused kernel of this block stamps its phases into the debug trace buffer
   int xdw = 1;         // 1: blocks with a kernels_xdw.cuh plan run expand + depthwise + pooling fused
   int dw_impl = 1;     // depthwise of the small-spatial blocks: 0 = rolling window + k_se_gate, 1 = k_dw_tile + k_se_fc2
   // debugging aid (cosyb200_debug_dump): copies of block `dump_block`'s internal tensors

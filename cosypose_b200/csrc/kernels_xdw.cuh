@@ -8,19 +8,25 @@
 // Reference op chain: models/efficientnet.py:71-90 (expand conv + BN + swish, depthwise conv + BN + swish,
 // adaptive_avg_pool2d of the squeeze-excite branch); static "same" padding models/efficientnet_utils.py:123-146:
 // the zero padding applies to the EXPANDED activation, so halo pixels outside the image are exact zeros in E.
+// That mask costs nothing here: the expand bias rides in the GEMM (A gets a column of ones at k = Cin, the weights
+// a row of biases), an out-of-image pixel is an all-zero A row, its accumulator is exactly 0 and swish(0) = 0.
 //
-// One CTA per SM, persistent over items = (hypothesis, spatial tile); an item walks over all chunks of 64 expanded
-// channels:
+// One CTA per SM, persistent over items = (hypothesis, spatial tile); an item walks over all chunks of `cc`
+// (48 or 64) expanded channels:
 //   workers (16 warps)  per item: x rows of the halo tile -> fp16 hi/lo split -> TMEM (A operand, resident for all
-//                       chunks; thread = tile row = TMEM lane);
-//                       per chunk: drain the accumulator (tcgen05.ld), bias + swish, zero the out-of-image rows,
-//                       -> shared-memory tile E[pixel][channel]; then the depthwise convolution from shared memory
-//                       with a rolling register window (lane = channel, conflict free), bias + swish, 128-byte row
-//                       stores of D and the pooling partial sums.
+//                       chunks; thread = tile row = TMEM lane; double buffered, the next item's rows are loaded
+//                       and converted under the last chunk of the current item);
+//                       per chunk: drain the accumulator (tcgen05.ld), swish -> shared-memory tile E[pixel][channel];
+//                       then the depthwise convolution from shared memory with a rolling register window (lane =
+//                       channel PAIR: 64-bit conflict-free loads, packed FFMA2), bias + swish, 256-byte row stores
+//                       of D and the pooling partial sums.
 //   warp 16             MMA issuer: per chunk and m-tile 3 * Kp/16 kind::f16 MMAs (a_lo*b_hi, a_hi*b_lo, then a_hi*b_hi),
 //                       A from TMEM, B from shared memory; accumulators double buffered in TMEM so the MMAs of chunk
 //                       c+1 run under the CUDA-core work of chunk c.
 //   warp 17             weight loader: one bulk copy (cp.async.bulk + mbarrier) per chunk into a 2-slot ring.
+// The kernel is bound by CUDA-core issue and the MUFU pipe (two swishes per expanded element), not by HBM or the
+// tensor pipe: swish is evaluated on pairs with ONE reciprocal (1 / (d0 * d1), then * d1 and * d0), 1.5 MUFU ops
+// per element instead of 2.
 // Precision: as kernels_pw2.cuh (fp16 hi/lo split of both operands, power-of-two weight scale, fp32 accumulate).
 #pragma once
 #include "kernels_pw2.cuh"
@@ -33,7 +39,6 @@ using pw2::make_desc;
 using pw2::make_idesc_f16;
 using pw2::pack_f16x2;
 using pw2::split11;
-using pw2::tmem_ld16_nowait;
 using pw2::tmem_ld_wait;
 using pw2::umma_commit_elect;
 using pw2::umma_f16_ts_pred;
@@ -41,49 +46,105 @@ using pw2::umma_f16_ts_pred;
 constexpr int NWW = 16;                 // worker warps
 constexpr int WORKERS = NWW * 32;
 constexpr int MMA_WARP = NWW, LOADER_WARP = NWW + 1;
-constexpr int THREADS = (NWW + 2) * 32;
-constexpr int CC = 64;                  // expanded channels per chunk (= MMA N)
-constexpr int EP = CC + 4;              // floats per E row: 16-byte row stores of 8 consecutive rows are conflict free
+constexpr int THREADS = (NWW + 4) * 32;      // warps 18-19 only complete the fifth warpgroup (setmaxnreg is per warpgroup)
+constexpr int CC_MAX = 64;              // expanded channels per chunk (= MMA N): 48 or 64
 constexpr int E_SLACK_ROWS = 16;        // the last x-segment of a tile may read (never use) a few pixels past the tile
-constexpr int MAX_UNITS = 64;
+constexpr int MAX_UNITS = 32;
+constexpr int MAX_XU = 2;               // 16-k units of the A row a worker thread converts
 constexpr uint32_t TMEM_COLS = 512;
 
 struct Plan {
-  int ok, MT, TH, TW, IH, IW, tiles_y, tiles_x, n_chunks, Kp, NX, NYS, smem_bytes;
+  int ok, MT, TH, TW, IH, IW, tiles_y, tiles_x, cc, n_chunks, Kp, NX, NYS, smem_bytes;
 };
+
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk2(float a, float b) {
+  u64 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void upk2(u64 r, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(r)); }
+__device__ __forceinline__ u64 ffma2(u64 a, u64 b, u64 c) {
+  u64 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ u64 fmul2(u64 a, u64 b) {
+  u64 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ u64 fadd2(u64 a, u64 b) {
+  u64 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ float ex2f(float t) {
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t));
+  return e;
+}
+__device__ __forceinline__ float rcpf(float d) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
+  return r;
+}
+// (swish(v0), swish(v1)) with one reciprocal: 1/d0 = d1 / (d0 d1).  The exponent is clamped so that d0 * d1 stays
+// finite (for v < -55 the result is |v| 2^-80 instead of |v| e^v: both far below one ulp of anything they are added to).
+__device__ __forceinline__ u64 swish2(u64 v) {
+  const u64 t = fmul2(v, pk2(-1.4426950408889634f, -1.4426950408889634f));
+  float t0, t1;
+  upk2(t, t0, t1);
+  const float d0 = 1.0f + ex2f(fminf(t0, 80.f)), d1 = 1.0f + ex2f(fminf(t1, 80.f));
+  const float r = rcpf(d0 * d1);
+  return fmul2(v, pk2(r * d1, r * d0));
+}
 
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* v) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]),
                "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
                : "memory");
 }
+// 8 consecutive accumulator columns as 4 packed pairs
+__device__ __forceinline__ void tmem_ld8_pairs(uint32_t taddr, u64* v) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+  tmem_ld_wait();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) asm("mov.b64 %0, {%1, %2};" : "=l"(v[i]) : "r"(r[2 * i]), "r"(r[2 * i + 1]));
+}
 
-// Wx: [n_chunks][hi|lo][Kp/8][CC][8] fp16 (rows >= Cexp zero); ebias [n_chunks*CC] (zero padded)
+// Wx: [n_chunks][hi|lo][Kp/8][cc][8] fp16, k = Cin holds the bias row, k > Cin zero
 // x [B][H][W][Cin], out [B][Ho][Wo][Cexp], partial [B][tiles][Cexp]
-template <int KS, int S, int NX>
+template <int KS, int S, int NX, int CCT>
 __global__ void __launch_bounds__(THREADS, 1)
-k_xdw(const float* __restrict__ x, const __half* __restrict__ Wx, const float* __restrict__ ebias, float inv_wscale,
-      const float* __restrict__ dw_w, const float* __restrict__ dw_bias, float* __restrict__ out,
-      float* __restrict__ partial, int B, int H, int W, int Cin, int Cexp, int Ho, int Wo, int pad, int MT, int TH,
-      int TW, int IH, int IW, int tiles_y, int tiles_x, int n_chunks, int Kp, int NYS) {
+k_xdw(const float* __restrict__ x, const __half* __restrict__ Wx, float inv_wscale, const float* __restrict__ dw_w,
+      const float* __restrict__ dw_bias, float* __restrict__ out, float* __restrict__ partial, int B, int H, int W,
+      int Cin, int Cexp, int Ho, int Wo, int pad, int MT, int TH, int TW, int IH, int IW, int tiles_y, int tiles_x,
+      int n_chunks, int Kp, int NYS, int do_trace) {
+  constexpr int cc = CCT;                                           // expanded channels per chunk (MMA N)
   constexpr int NSLOT = (KS + S - 1) / S;
   constexpr int PERIOD = S * NSLOT;
   constexpr int NIN = (NX - 1) * S + KS;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[10];
   __shared__ uint32_t s_tmem;
-  __shared__ __align__(16) float s_ebias[CC];
-  __shared__ float s_ps[MAX_UNITS * 32];
+  __shared__ __align__(8) float s_ps[MAX_UNITS * 64];
   const uint32_t b_base = (smem_u32(smem_raw) + 127u) & ~127u;
-  const uint32_t b_bytes = (uint32_t)Kp * CC * 4u;                  // hi + lo image of one chunk
-  float* E = reinterpret_cast<float*>(smem_raw + (b_base - smem_u32(smem_raw)) + 2 * b_bytes);
+  const uint32_t b_bytes = (uint32_t)Kp * cc * 4u;                  // hi + lo image of one chunk
+  const uint32_t e_base = b_base + 2 * b_bytes;
+  constexpr int EP = cc + 4;                                        // floats per E row (16-byte row stores conflict free)
   const int tid = threadIdx.x, lane = tid % 32;
   const int warp = __shfl_sync(0xffffffffu, tid / 32, 0);
   const int tiles = tiles_y * tiles_x;
   const int n_items = B * tiles;
   const int n_rows = IH * IW;
-  const uint32_t ACC_STRIDE = (uint32_t)MT * CC;                    // columns of one accumulator buffer
+  const uint32_t ACC_STRIDE = (uint32_t)MT * cc;                    // columns of one accumulator buffer
   const uint32_t A_COL0 = 2 * ACC_STRIDE;
+  const uint32_t A_STRIDE = (uint32_t)MT * Kp;                      // columns of one A buffer
   auto fullA = [&]() { return smem_u32(&bars[0]); };
   auto fullB = [&](int s) { return smem_u32(&bars[1 + s]); };
   auto emptyB = [&](int s) { return smem_u32(&bars[3 + s]); };
@@ -107,6 +168,7 @@ k_xdw(const float* __restrict__ x, const __half* __restrict__ Wx, const float* _
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, s_tmem, 0);
 
   if (warp < NWW) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");   // 16 x 32 x (112 - 96) = what the fifth warpgroup releases (96 -> 32)
     // ------------------------------------------------------------------ workers
     const int q = warp % 4, part = warp / 4;
     const int nsub = 4 / MT;                                   // sub-parts (k units / column ranges) per m-tile
@@ -115,155 +177,209 @@ k_xdw(const float* __restrict__ x, const __half* __restrict__ Wx, const float* _
     const int row = mt * 128 + q * 32 + lane;                  // tile row (halo pixel) == TMEM lane of m-tile mt
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
     const int py = row / IW, px = row % IW;
-    const int CW = CC / nsub;                                  // accumulator columns this thread drains per chunk
-    int gch = 0;                                               // chunks processed by this CTA so far
-    int local_it = 0;
-    for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++local_it) {
+    const int CW = cc / nsub;                                  // accumulator columns this thread drains per chunk
+    const int n_xu = Kp / 16;
+    float xv[MAX_XU][16];
+    bool x_valid = false;
+
+    // this thread's k units of its halo pixel of item `it`, global -> registers (+ the ones column at k = Cin)
+    auto load_x = [&](int it) {
       const int img = it / tiles, tile = it % tiles;
-      const int oy0 = (tile / tiles_x) * TH, ox0 = (tile % tiles_x) * TW;
-      const int gy = oy0 * S - pad + py, gx = ox0 * S - pad + px;
-      const bool row_valid = row < n_rows && gy >= 0 && gy < H && gx >= 0 && gx < W;
-      // ---- A operand: this thread's halo pixel, 16 k per unit, -> hi/lo fp16 -> TMEM
+      const int gy = (tile / tiles_x) * TH * S - pad + py, gx = (tile % tiles_x) * TW * S - pad + px;
+      x_valid = row < n_rows && gy >= 0 && gy < H && gx >= 0 && gx < W;
+      const float* xr = x + (((size_t)img * H + (x_valid ? gy : 0)) * W + (x_valid ? gx : 0)) * Cin;
+#pragma unroll
+      for (int j = 0; j < MAX_XU; ++j) {
+        const int u = sub + j * nsub;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (part_on && x_valid && u * 16 + c * 4 < Cin) t = __ldg(reinterpret_cast<const float4*>(xr + u * 16 + c * 4));
+          xv[j][c * 4] = t.x; xv[j][c * 4 + 1] = t.y; xv[j][c * 4 + 2] = t.z; xv[j][c * 4 + 3] = t.w;
+        }
+      }
+    };
+    // registers -> hi/lo fp16 -> TMEM A buffer `ab`
+    auto convert_x = [&](int ab) {
       if (part_on) {
-        const float* xr = x + (((size_t)img * H + (row_valid ? gy : 0)) * W + (row_valid ? gx : 0)) * Cin;
-        for (int u = sub; u < Kp / 16; u += nsub) {
-          float v[16];
+        const float one = x_valid ? 1.f : 0.f;
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (row_valid && u * 16 + c * 4 < Cin) t = __ldg(reinterpret_cast<const float4*>(xr + u * 16 + c * 4));
-            v[c * 4] = t.x; v[c * 4 + 1] = t.y; v[c * 4 + 2] = t.z; v[c * 4 + 3] = t.w;
-          }
-          uint32_t ph[8], pl[8];
+        for (int j = 0; j < MAX_XU; ++j) {
+          const int u = sub + j * nsub;
+          if (u < n_xu) {
+            if (Cin == u * 16) xv[j][0] = one;
+            else if (Cin == u * 16 + 8) xv[j][8] = one;
+            uint32_t ph[8], pl[8];
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            float h0, l0, h1, l1;
-            split11(v[2 * c], h0, l0);
-            split11(v[2 * c + 1], h1, l1);
-            ph[c] = pack_f16x2(h0, h1);
-            pl[c] = pack_f16x2(l0, l1);
+            for (int c = 0; c < 8; ++c) {
+              float h0, l0, h1, l1;
+              split11(xv[j][2 * c], h0, l0);
+              split11(xv[j][2 * c + 1], h1, l1);
+              ph[c] = pack_f16x2(h0, h1);
+              pl[c] = pack_f16x2(l0, l1);
+            }
+            const uint32_t a_hi = t_lane + A_COL0 + ab * A_STRIDE + (uint32_t)(mt * Kp) + (uint32_t)(u * 8);
+            tmem_st8(a_hi, ph);
+            tmem_st8(a_hi + (uint32_t)(Kp / 2), pl);
           }
-          const uint32_t a_hi = t_lane + A_COL0 + (uint32_t)(mt * Kp) + (uint32_t)(u * 8);
-          tmem_st8(a_hi, ph);
-          tmem_st8(a_hi + (uint32_t)(Kp / 2), pl);
         }
         tmem_st_wait();
       }
       tc_fence_before();
       mbar_arrive(fullA());
+    };
 
+    const int NXS = (TW + NX - 1) / NX;
+    const int RH = (TH + NYS - 1) / NYS;
+    const int n_units = NXS * NYS;
+    int gch = 0;                                               // chunks processed by this CTA so far
+    int local_it = 0;
+    if ((int)blockIdx.x < n_items) {
+      load_x(blockIdx.x);
+      convert_x(0);
+    }
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++local_it) {
+      const int img = it / tiles, tile = it % tiles;
+      const int oy0 = (tile / tiles_x) * TH, ox0 = (tile % tiles_x) * TW;
+      const int next = it + gridDim.x;
       for (int ch = 0; ch < n_chunks; ++ch, ++gch) {
         const int buf = gch & 1;
-        const int cc_here = min(CC, Cexp - ch * CC);
-        if (tid < CC) s_ebias[tid] = __ldg(ebias + ch * CC + tid);   // read after barrier #0 below
+        const bool prep_next = ch == n_chunks - 1 && next < n_items;
+        const bool tr = do_trace && tid == 0 && gch < 16;
+        if (tr) trace(512 + 8 * gch);
+        if (prep_next) load_x(next);                            // in flight under the accumulator wait and the drain
+        // depthwise taps and bias of this lane's channel pair (the same for every unit of the chunk)
+        const int c_local = 2 * lane;
+        const int c_glob = ch * cc + c_local;
+        const bool c_ok = c_local < cc;
+        u64 wreg[KS * KS];
+        u64 bv2;
+        auto load_w = [&]() {
+#pragma unroll
+          for (int t = 0; t < KS * KS; ++t)
+            wreg[t] = c_ok ? __ldg(reinterpret_cast<const u64*>(dw_w + (size_t)t * Cexp + c_glob)) : 0ull;
+          bv2 = c_ok ? __ldg(reinterpret_cast<const u64*>(dw_bias + c_glob)) : 0ull;
+        };
+        if (!prep_next) load_w();                               // (with prep_next the registers hold the next item's rows)
         mbar_wait_warp(acc_full(buf), (gch >> 1) & 1);
         tc_fence_after();
-        named_bar_sync(1, WORKERS);                                   // #0: s_ebias visible, previous chunk's readers done
-        // ---- drain: bias + swish, out-of-image rows are exact zeros
+        if (tr) trace(512 + 8 * gch + 1);
+        // ---- drain: swish of the accumulator (bias included, out-of-image rows are exact zeros)
         if (part_on) {
-          float* erow = E + (size_t)row * EP + sub * CW;
-          const uint32_t t_acc = t_lane + buf * ACC_STRIDE + (uint32_t)(mt * CC + sub * CW);
-          for (int c0 = 0; c0 < CW; c0 += 16) {
-            float v[16];
-            tmem_ld16_nowait(t_acc + c0, v);
-            tmem_ld_wait();
+          const uint32_t e_row = e_base + (uint32_t)(row * EP + sub * CW) * 4u;
+          const uint32_t t_acc = t_lane + buf * ACC_STRIDE + (uint32_t)(mt * cc + sub * CW);
+          const u64 inv2 = pk2(inv_wscale, inv_wscale);
+          for (int c0 = 0; c0 < CW; c0 += 8) {
+            u64 v[4];
+            tmem_ld8_pairs(t_acc + c0, v);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float o = swishf(fmaf(v[i], inv_wscale, s_ebias[sub * CW + c0 + i]));
-              v[i] = row_valid ? o : 0.f;
-            }
-#pragma unroll
-            for (int i = 0; i < 16; i += 4)
-              *reinterpret_cast<float4*>(erow + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            for (int i = 0; i < 4; ++i) v[i] = swish2(fmul2(v[i], inv2));
+            asm volatile("st.shared.v2.b64 [%0], {%1, %2};" ::"r"(e_row + c0 * 4), "l"(v[0]), "l"(v[1]) : "memory");
+            asm volatile("st.shared.v2.b64 [%0], {%1, %2};" ::"r"(e_row + c0 * 4 + 16), "l"(v[2]), "l"(v[3]) : "memory");
           }
         }
         tc_fence_before();
         mbar_arrive(acc_empty(buf));
-        named_bar_sync(1, WORKERS);                                   // #1: E complete
-        // ---- depthwise from E: unit = (32-channel group, x segment, y segment); lane = channel
-        const int n_groups = (cc_here + 31) / 32;
-        const int NXS = (TW + NX - 1) / NX;
-        const int RH = (TH + NYS - 1) / NYS;
-        const int n_units = n_groups * NXS * NYS;
+        if (tr) trace(512 + 8 * gch + 2);
+        if (prep_next) {                                        // the MMAs of the next item start under this chunk's dw
+          convert_x((local_it + 1) & 1);
+          load_w();
+        }
+        if (tr) trace(512 + 8 * gch + 3);
+        named_bar_sync(1, WORKERS);                             // #1: E complete
+        if (tr) trace(512 + 8 * gch + 4);
+        // ---- depthwise from E: unit = (x segment, y segment); lane = channel pair
         for (int u = warp; u < n_units; u += NWW) {
-          const int g = u % n_groups, xs = (u / n_groups) % NXS, ys = u / (n_groups * NXS);
-          const int c_local = g * 32 + lane;
-          const int c_glob = ch * CC + c_local;
-          const bool c_ok = c_local < cc_here;
+          const int xs = u % NXS, ys = u / NXS;
           const int oyr0 = ys * RH, oxr0 = xs * NX;
           const int rows_here = min(RH, min(TH, Ho - oy0) - oyr0);
-          float wreg[KS * KS];
-#pragma unroll
-          for (int t = 0; t < KS * KS; ++t) wreg[t] = c_ok ? __ldg(dw_w + (size_t)t * Cexp + c_glob) : 0.f;
-          const float bv = c_ok ? __ldg(dw_bias + c_glob) : 0.f;
-          float acc[NSLOT][NX];
+          u64 acc[NSLOT][NX];
 #pragma unroll
           for (int s = 0; s < NSLOT; ++s)
 #pragma unroll
-            for (int xx = 0; xx < NX; ++xx) acc[s][xx] = 0.f;
-          float psum = 0.f;
-          const float* e0 = E + ((size_t)(oyr0 * S) * IW + oxr0 * S) * EP + c_local;
-          float* o0 = out + (((size_t)img * Ho + oy0 + oyr0) * Wo + ox0 + oxr0) * Cexp + c_glob;
+            for (int xx = 0; xx < NX; ++xx) acc[s][xx] = bv2;
+          u64 psum = 0ull;
+          bool x_ok[NX];
+#pragma unroll
+          for (int xx = 0; xx < NX; ++xx) x_ok[xx] = c_ok && oxr0 + xx < TW && ox0 + oxr0 + xx < Wo;
+          uint32_t e_ptr = e_base + (uint32_t)(((oyr0 * S) * IW + oxr0 * S) * EP + c_local) * 4u;
+          const uint32_t e_row_bytes = (uint32_t)(IW * EP) * 4u;
+          constexpr uint32_t e_px_bytes = (uint32_t)EP * 4u;
+          float* o_ptr = out + (((size_t)img * Ho + oy0 + oyr0) * Wo + ox0 + oxr0) * Cexp + c_glob;
+          const int o_row = Wo * Cexp;
           const int n_in_rows = rows_here > 0 ? (rows_here - 1) * S + KS : 0;
+          const int out_span = rows_here * S;
           for (int r0 = 0; r0 < n_in_rows; r0 += PERIOD) {
 #pragma unroll
             for (int j = 0; j < PERIOD; ++j) {
               const int r = r0 + j;
               if (r < n_in_rows) {
-                float v[NIN];
+                u64 v[NIN];
 #pragma unroll
-                for (int kx = 0; kx < NIN; ++kx) v[kx] = e0[((size_t)r * IW + kx) * EP];
+                for (int kx = 0; kx < NIN; ++kx)
+                  asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v[kx]) : "r"(e_ptr + kx * e_px_bytes));
+                e_ptr += e_row_bytes;
 #pragma unroll
                 for (int ky = 0; ky < KS; ++ky) {
-                  if ((j - ky + PERIOD * KS) % S == 0) {
+                  if ((j - ky + PERIOD * KS) % S == 0 && r >= ky && r - ky < out_span) {   // feeds a row this unit owns
                     const int slot = ((j - ky + PERIOD * KS) / S) % NSLOT;
 #pragma unroll
                     for (int xx = 0; xx < NX; ++xx)
 #pragma unroll
                       for (int kx = 0; kx < KS; ++kx)
-                        acc[slot][xx] = fmaf(v[xx * S + kx], wreg[ky * KS + kx], acc[slot][xx]);
+                        acc[slot][xx] = ffma2(v[xx * S + kx], wreg[ky * KS + kx], acc[slot][xx]);
                   }
                 }
               }
               if ((j - (KS - 1) + PERIOD * KS) % S == 0) {
                 const int slot_done = ((j - (KS - 1) + PERIOD * KS) / S) % NSLOT;
                 const int num = r - (KS - 1);
-                const int oyr = num >= 0 ? num / S : -1;
-                if (oyr >= 0 && oyr < rows_here && c_ok) {
+                if (num >= 0 && num < rows_here * S) {             // output row num / S is complete
+                  u64 o[NX];
+#pragma unroll
+                  for (int xx = 0; xx < NX; ++xx) o[xx] = swish2(acc[slot_done][xx]);
 #pragma unroll
                   for (int xx = 0; xx < NX; ++xx) {
-                    if (oxr0 + xx < TW && ox0 + oxr0 + xx < Wo) {
-                      const float o = swishf(acc[slot_done][xx] + bv);
-                      psum += o;
-                      o0[((size_t)oyr * Wo + xx) * Cexp] = o;
+                    if (x_ok[xx]) {
+                      psum = fadd2(psum, o[xx]);
+                      float a, b;
+                      upk2(o[xx], a, b);
+                      *reinterpret_cast<float2*>(o_ptr + xx * Cexp) = make_float2(a, b);
                     }
                   }
+                  o_ptr += o_row;
                 }
 #pragma unroll
-                for (int xx = 0; xx < NX; ++xx) acc[slot_done][xx] = 0.f;
+                for (int xx = 0; xx < NX; ++xx) acc[slot_done][xx] = bv2;
               }
             }
           }
-          s_ps[u * 32 + lane] = psum;
+          float pa, pb;
+          upk2(psum, pa, pb);
+          *reinterpret_cast<float2*>(&s_ps[u * 64 + c_local]) = make_float2(pa, pb);
         }
-        named_bar_sync(1, WORKERS);                                   // #2: E consumed, s_ps complete
-        if (tid < cc_here) {
-          const int g = tid / 32, l = tid % 32;
+        if (tr) trace(512 + 8 * gch + 5);
+        named_bar_sync(1, WORKERS);                             // #2: E consumed, s_ps complete
+        if (tr) trace(512 + 8 * gch + 6);
+        if (tid < cc) {
           float s = 0.f;
-          for (int v = 0; v < NXS * NYS; ++v) s += s_ps[(v * n_groups + g) * 32 + l];
-          partial[((size_t)img * tiles + tile) * Cexp + ch * CC + tid] = s;
+          for (int v = 0; v < n_units; ++v) s += s_ps[v * 64 + tid];
+          partial[((size_t)img * tiles + tile) * Cexp + ch * cc + tid] = s;
         }
       }
     }
-  } else if (warp == MMA_WARP) {
+  } else {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+  if (warp == MMA_WARP) {
     // ------------------------------------------------------------------ MMA issuer
-    const uint32_t idesc = make_idesc_f16(CC);
-    const uint32_t lbo = (uint32_t)CC * 16u;
+    const uint32_t idesc = make_idesc_f16(cc);
+    const uint32_t lbo = (uint32_t)cc * 16u;
     const int ksteps = Kp / 16;
     int gch = 0, local_it = 0;
     for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++local_it) {
       mbar_wait_warp(fullA(), local_it & 1);
       tc_fence_after();
+      const uint32_t a_base = tmem_base + A_COL0 + (local_it & 1) * A_STRIDE;
       for (int ch = 0; ch < n_chunks; ++ch, ++gch) {
         const int buf = gch & 1;
         mbar_wait_warp(fullB(buf), (gch >> 1) & 1);
@@ -272,8 +388,8 @@ k_xdw(const float* __restrict__ x, const __half* __restrict__ Wx, const float* _
         const uint32_t b_hi = b_base + buf * b_bytes, b_lo = b_hi + b_bytes / 2;
         const uint64_t dbh0 = make_desc(b_hi, lbo, 128), dbl0 = make_desc(b_lo, lbo, 128);
         for (int m = 0; m < MT; ++m) {
-          const uint32_t d = tmem_base + buf * ACC_STRIDE + (uint32_t)(m * CC);
-          const uint32_t a_hi = tmem_base + A_COL0 + (uint32_t)(m * Kp), a_lo = a_hi + (uint32_t)(Kp / 2);
+          const uint32_t d = tmem_base + buf * ACC_STRIDE + (uint32_t)(m * cc);
+          const uint32_t a_hi = a_base + (uint32_t)(m * Kp), a_lo = a_hi + (uint32_t)(Kp / 2);
           for (int j = 0; j < ksteps; ++j) {                       // small terms first
             const uint64_t koff = (uint64_t)((j * 2 * lbo) >> 4);
             umma_f16_ts_pred(d, a_lo + j * 8, dbh0 + koff, idesc, j == 0 ? 0u : 1u);
@@ -290,7 +406,7 @@ k_xdw(const float* __restrict__ x, const __half* __restrict__ Wx, const float* _
       }
     }
     tc_fence_before();
-  } else {
+  } else if (warp == LOADER_WARP) {
     // ------------------------------------------------------------------ weight loader
     if (lane == 0) {
       int gch = 0;
@@ -299,10 +415,11 @@ k_xdw(const float* __restrict__ x, const __half* __restrict__ Wx, const float* _
           const int slot = gch & 1;
           if (gch >= 2) mbar_wait(emptyB(slot), ((gch >> 1) - 1) & 1);
           mbar_arrive_expect_tx(fullB(slot), b_bytes);
-          bulk_copy_g2s(b_base + slot * b_bytes, Wx + (size_t)ch * Kp * CC * 2, b_bytes, fullB(slot));
+          bulk_copy_g2s(b_base + slot * b_bytes, Wx + (size_t)ch * Kp * cc * 2, b_bytes, fullB(slot));
         }
       }
     }
+  }
   }
   tc_fence_before();
   __syncthreads();
@@ -313,44 +430,58 @@ k_xdw(const float* __restrict__ x, const __half* __restrict__ Wx, const float* _
 }
 
 // ---- host side ---------------------------------------------------------------------------------------
-inline int kp_for(int cin) { return (cin + 15) / 16 * 16; }
-inline int n_chunks_for(int cexp) { return (cexp + CC - 1) / CC; }
+inline int kp_for(int cin) { return (cin + 1 + 15) / 16 * 16; }   // + the ones column that carries the bias
 
 // tile shapes chosen so that the halo tile fills two 128-row MMA tiles; blocks whose input has too many channels
-// for a TMEM-resident A operand (MT * (128 + Kp) > 512) are not planned
+// for two TMEM-resident A buffers (MT * (2 cc + 2 Kp) > 512) are not planned
 inline Plan make_plan(const BlockSpec& b) {
   Plan p{};
   if (b.e == 1) return p;
   p.Kp = kp_for(b.cin);
-  p.n_chunks = n_chunks_for(b.cexp);
+  p.cc = b.cexp % 64 == 0 ? 64 : 48;
+  if (b.cexp % p.cc) return p;
+  p.n_chunks = b.cexp / p.cc;
   p.MT = 2;
-  if (b.k == 3 && b.s == 2 && b.hout == 60) { p.TH = 6; p.TW = 8; p.NX = 2; p.NYS = 2; }          // block 2
-  else if (b.k == 3 && b.s == 1 && b.hout == 60) { p.TH = 12; p.TW = 16; p.NX = 4; p.NYS = 2; }   // blocks 3-4
-  else if (b.k == 5 && b.s == 2 && b.hout == 30) { p.TH = 5; p.TW = 8; p.NX = 2; p.NYS = 2; }     // block 5
-  else if (b.k == 5 && b.s == 1 && b.hout == 30) { p.TH = 10; p.TW = 14; p.NX = 4; p.NYS = 2; }   // blocks 6-7
-  else if (b.k == 3 && b.s == 2 && b.hout == 15) { p.TH = 5; p.TW = 10; p.NX = 2; p.NYS = 2; }    // block 8
+  if (b.k == 3 && b.s == 2 && b.hout == 60) { p.TH = 6; p.TW = 8; p.NX = 1; p.NYS = 2; }          // block 2
+  else if (b.k == 3 && b.s == 1 && b.hout == 60) { p.TH = 12; p.TW = 16; p.NX = 2; p.NYS = 2; }   // blocks 3-4
+  else if (b.k == 5 && b.s == 2 && b.hout == 30) { p.TH = 5; p.TW = 8; p.NX = 1; p.NYS = 2; }     // block 5
+  else if (b.k == 5 && b.s == 1 && b.hout == 30) { p.TH = 10; p.TW = 14; p.NX = 2; p.NYS = 2; }   // blocks 6-7
+  else if (b.k == 3 && b.s == 2 && b.hout == 15) { p.TH = 5; p.TW = 10; p.NX = 2; p.NYS = 3; }    // block 8
   else return p;
   p.IH = (p.TH - 1) * b.s + b.k;
   p.IW = (p.TW - 1) * b.s + b.k;
-  if (p.IH * p.IW > p.MT * 128 || p.MT * (128 + p.Kp) > 512) return p;
+  if (p.IH * p.IW > p.MT * 128 || p.MT * (2 * p.cc + 2 * p.Kp) > 512) return p;
+  if (p.Kp / 16 > MAX_XU * (4 / p.MT)) return p;
   p.tiles_y = (b.hout + p.TH - 1) / p.TH;
   p.tiles_x = (b.wout + p.TW - 1) / p.TW;
-  p.smem_bytes = 128 + 2 * p.Kp * CC * 4 + (p.MT * 128 + E_SLACK_ROWS) * EP * 4;
+  if (((p.TW + p.NX - 1) / p.NX) * p.NYS > MAX_UNITS) return p;
+  p.smem_bytes = 128 + 2 * p.Kp * p.cc * 4 + (p.MT * 128 + E_SLACK_ROWS) * (p.cc + 4) * 4;
   p.ok = 1;
   return p;
 }
 
-// W_nk [Cexp][Cin] (BN scale folded) -> [n_chunks][hi|lo][Kp/8][CC][8] fp16 bits
-inline std::vector<uint16_t> pack_weights(const float* W_nk, int N, int K, float wscale) {
-  const int Kp = kp_for(K), nch = n_chunks_for(N);
-  std::vector<uint16_t> o((size_t)nch * 2 * (Kp / 8) * CC * 8, 0);
+// max |.| over the expand weights and their biases: one power-of-two scale serves both (the bias is a weight row)
+inline float weight_scale(const float* W_nk, const float* bias, int N, int K) {
+  float mx = 0.f;
+  for (size_t i = 0; i < (size_t)N * K; ++i) mx = std::max(mx, std::fabs(W_nk[i]));
+  for (int i = 0; i < N; ++i) mx = std::max(mx, std::fabs(bias[i]));
+  if (!(mx > 0.f) || !std::isfinite(mx)) return 1.f;
+  int e;
+  std::frexp(mx, &e);
+  return std::ldexp(1.f, 13 - e);
+}
+
+// W_nk [Cexp][Cin] (BN scale folded), bias [Cexp] -> [n_chunks][hi|lo][Kp/8][cc][8] fp16 bits, bias at k = Cin
+inline std::vector<uint16_t> pack_weights(const float* W_nk, const float* bias, int N, int K, int cc, float wscale) {
+  const int Kp = kp_for(K), nch = N / cc;
+  std::vector<uint16_t> o((size_t)nch * 2 * (Kp / 8) * cc * 8, 0);
   for (int n = 0; n < N; ++n)
-    for (int k = 0; k < K; ++k) {
-      const float w = W_nk[(size_t)n * K + k] * wscale;
+    for (int k = 0; k <= K; ++k) {
+      const float w = (k < K ? W_nk[(size_t)n * K + k] : bias[n]) * wscale;
       const float h = pw2::host_round11(w);
-      const int ch = n / CC, nn = n % CC;
-      const size_t hi = ((((size_t)ch * 2 + 0) * (Kp / 8) + k / 8) * CC + nn) * 8 + k % 8;
-      const size_t lo = ((((size_t)ch * 2 + 1) * (Kp / 8) + k / 8) * CC + nn) * 8 + k % 8;
+      const int ch = n / cc, nn = n % cc;
+      const size_t hi = ((((size_t)ch * 2 + 0) * (Kp / 8) + k / 8) * cc + nn) * 8 + k % 8;
+      const size_t lo = ((((size_t)ch * 2 + 1) * (Kp / 8) + k / 8) * cc + nn) * 8 + k % 8;
       o[hi] = pw2::host_f16_bits(h);
       o[lo] = pw2::host_f16_bits(w - h);
     }
