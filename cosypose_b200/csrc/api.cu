@@ -283,11 +283,11 @@ static bool use_dw_tile(const cosyb200_handle* h, const BlockSpec& b) {
 // fused expand + depthwise + pooling (kernels_xdw.cuh)
 static bool use_xdw(const cosyb200_handle* h, const BlockSpec& b) { return h->xdw != 0 && xdw::make_plan(b).ok; }
 
-template <int KS, int S, int NX, int CCT>
+template <int KS, int S, int NX, int CCT, int RH>
 static int launch_xdw_inst(const xdw::Plan& p, cosyb200_handle* h, const BlockSpec& b, const BlockWeights& w,
                            const float* x, float* out, int B, cudaStream_t st) {
   const int n_items = B * p.tiles_y * p.tiles_x;
-  xdw::k_xdw<KS, S, NX, CCT><<<std::min(n_items, h->n_sms), xdw::THREADS, p.smem_bytes, st>>>(
+  xdw::k_xdw<KS, S, NX, CCT, RH><<<std::min(n_items, h->n_sms), xdw::THREADS, p.smem_bytes, st>>>(
       x, (const __half*)w.expand_x, w.expand_x_inv, w.dw_w, w.dw_bias, out, h->pool_partial, B, b.hin, b.win, b.cin,
       b.cexp, b.hout, b.wout, b.pad_lo, p.MT, p.TH, p.TW, p.IH, p.IW, p.tiles_y, p.tiles_x, p.n_chunks, p.Kp,
       p.NYS, h->cur_block == h->trace_block ? 1 : 0);
@@ -298,8 +298,8 @@ static int launch_xdw_inst(const xdw::Plan& p, cosyb200_handle* h, const BlockSp
 static int launch_xdw(cosyb200_handle* h, const BlockSpec& b, const BlockWeights& w, const float* x, float* out, int B,
                       cudaStream_t st) {
   const xdw::Plan p = xdw::make_plan(b);
-#define XDW(KS, S, NXV, CCV) if (b.k == KS && b.s == S && p.NX == NXV && p.cc == CCV) return launch_xdw_inst<KS, S, NXV, CCV>(p, h, b, w, x, out, B, st)
-  XDW(3, 2, 1, 48); XDW(3, 1, 2, 64); XDW(5, 2, 1, 64); XDW(5, 1, 2, 48); XDW(3, 2, 2, 48);
+#define XDW(KS, S, NXV, CCV, RHV) if (b.k == KS && b.s == S && p.NX == NXV && p.cc == CCV && p.RH == RHV) return launch_xdw_inst<KS, S, NXV, CCV, RHV>(p, h, b, w, x, out, B, st)
+  XDW(3, 2, 1, 48, 3); XDW(3, 1, 2, 64, 6); XDW(5, 2, 1, 64, 3); XDW(5, 1, 2, 48, 5); XDW(3, 2, 2, 48, 2);
 #undef XDW
   set_error("launch_xdw: no instance for k=%d s=%d NX=%d", b.k, b.s, p.NX);
   return COSYB200_EINVAL;
@@ -473,11 +473,11 @@ int cosyb200_create(cosyb200_handle** out, int device, int max_batch) {
     rc |= opt_in_gemm_kernels<true, false, false>();
     rc |= opt_in_gemm_kernels<true, false, true>();
     rc |= opt_in_gemm_kernels<false, false, false>();
-    rc |= opt_in_smem(xdw::k_xdw<3, 2, 1, 48>, 200 * 1024);
-    rc |= opt_in_smem(xdw::k_xdw<3, 1, 2, 64>, 200 * 1024);
-    rc |= opt_in_smem(xdw::k_xdw<5, 2, 1, 64>, 200 * 1024);
-    rc |= opt_in_smem(xdw::k_xdw<5, 1, 2, 48>, 200 * 1024);
-    rc |= opt_in_smem(xdw::k_xdw<3, 2, 2, 48>, 200 * 1024);
+    rc |= opt_in_smem(xdw::k_xdw<3, 2, 1, 48, 3>, 200 * 1024);
+    rc |= opt_in_smem(xdw::k_xdw<3, 1, 2, 64, 6>, 200 * 1024);
+    rc |= opt_in_smem(xdw::k_xdw<5, 2, 1, 64, 3>, 200 * 1024);
+    rc |= opt_in_smem(xdw::k_xdw<5, 1, 2, 48, 5>, 200 * 1024);
+    rc |= opt_in_smem(xdw::k_xdw<3, 2, 2, 48, 2>, 200 * 1024);
     rc |= opt_in_smem(k_roi_crop, (int)(CROP_SMEM_FLOATS * sizeof(float)));
     rc |= opt_in_smem(k_se_gate, 100 * 1024);
     rc |= opt_in_smem(k_dw_tile<5, 1, 40, 1>, 80 * 1024);

@@ -54,7 +54,7 @@ constexpr int MAX_XU = 2;               // 16-k units of the A row a worker thre
 constexpr uint32_t TMEM_COLS = 512;
 
 struct Plan {
-  int ok, MT, TH, TW, IH, IW, tiles_y, tiles_x, cc, n_chunks, Kp, NX, NYS, smem_bytes;
+  int ok, MT, TH, TW, IH, IW, tiles_y, tiles_x, cc, n_chunks, Kp, NX, NYS, RH, smem_bytes;
 };
 
 typedef unsigned long long u64;
@@ -119,15 +119,13 @@ __device__ __forceinline__ void tmem_ld8_pairs(uint32_t taddr, u64* v) {
 
 // Wx: [n_chunks][hi|lo][Kp/8][cc][8] fp16, k = Cin holds the bias row, k > Cin zero
 // x [B][H][W][Cin], out [B][Ho][Wo][Cexp], partial [B][tiles][Cexp]
-template <int KS, int S, int NX, int CCT>
+template <int KS, int S, int NX, int CCT, int RH>
 __global__ void __launch_bounds__(THREADS, 1)
 k_xdw(const float* __restrict__ x, const __half* __restrict__ Wx, float inv_wscale, const float* __restrict__ dw_w,
       const float* __restrict__ dw_bias, float* __restrict__ out, float* __restrict__ partial, int B, int H, int W,
       int Cin, int Cexp, int Ho, int Wo, int pad, int MT, int TH, int TW, int IH, int IW, int tiles_y, int tiles_x,
       int n_chunks, int Kp, int NYS, int do_trace) {
   constexpr int cc = CCT;                                           // expanded channels per chunk (MMA N)
-  constexpr int NSLOT = (KS + S - 1) / S;
-  constexpr int PERIOD = S * NSLOT;
   constexpr int NIN = (NX - 1) * S + KS;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[10];
@@ -230,7 +228,6 @@ k_xdw(const float* __restrict__ x, const __half* __restrict__ Wx, float inv_wsca
     };
 
     const int NXS = (TW + NX - 1) / NX;
-    const int RH = (TH + NYS - 1) / NYS;
     const int n_units = NXS * NYS;
     int gch = 0;                                               // chunks processed by this CTA so far
     int local_it = 0;
@@ -293,64 +290,52 @@ k_xdw(const float* __restrict__ x, const __half* __restrict__ Wx, float inv_wsca
           const int xs = u % NXS, ys = u / NXS;
           const int oyr0 = ys * RH, oxr0 = xs * NX;
           const int rows_here = min(RH, min(TH, Ho - oy0) - oyr0);
-          u64 acc[NSLOT][NX];
+          // Fully unrolled over the NR input rows of the unit: every E value is loaded once and feeds the output rows
+          // it touches (known at compile time); the pre-activations of all RH x NX output pairs stay in registers,
+          // then all swishes are evaluated together (RH * NX independent chains for the MUFU latency).
+          constexpr int NR = (RH - 1) * S + KS;
+          u64 o[RH][NX];
 #pragma unroll
-          for (int s = 0; s < NSLOT; ++s)
+          for (int oy = 0; oy < RH; ++oy)
 #pragma unroll
-            for (int xx = 0; xx < NX; ++xx) acc[s][xx] = bv2;
-          u64 psum = 0ull;
-          bool x_ok[NX];
-#pragma unroll
-          for (int xx = 0; xx < NX; ++xx) x_ok[xx] = c_ok && oxr0 + xx < TW && ox0 + oxr0 + xx < Wo;
+            for (int xx = 0; xx < NX; ++xx) o[oy][xx] = bv2;
           uint32_t e_ptr = e_base + (uint32_t)(((oyr0 * S) * IW + oxr0 * S) * EP + c_local) * 4u;
           const uint32_t e_row_bytes = (uint32_t)(IW * EP) * 4u;
           constexpr uint32_t e_px_bytes = (uint32_t)EP * 4u;
+#pragma unroll
+          for (int r = 0; r < NR; ++r) {
+            u64 v[NIN];
+#pragma unroll
+            for (int kx = 0; kx < NIN; ++kx)
+              asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v[kx]) : "r"(e_ptr + kx * e_px_bytes));
+            e_ptr += e_row_bytes;
+#pragma unroll
+            for (int ky = 0; ky < KS; ++ky) {
+              if (r >= ky && (r - ky) % S == 0 && (r - ky) / S < RH) {
+                const int oy = (r - ky) / S;
+#pragma unroll
+                for (int xx = 0; xx < NX; ++xx)
+#pragma unroll
+                  for (int kx = 0; kx < KS; ++kx) o[oy][xx] = ffma2(v[xx * S + kx], wreg[ky * KS + kx], o[oy][xx]);
+              }
+            }
+          }
+#pragma unroll
+          for (int oy = 0; oy < RH; ++oy)
+#pragma unroll
+            for (int xx = 0; xx < NX; ++xx) o[oy][xx] = swish2(o[oy][xx]);
+          u64 psum = 0ull;
           float* o_ptr = out + (((size_t)img * Ho + oy0 + oyr0) * Wo + ox0 + oxr0) * Cexp + c_glob;
           const int o_row = Wo * Cexp;
-          const int n_in_rows = rows_here > 0 ? (rows_here - 1) * S + KS : 0;
-          const int out_span = rows_here * S;
-          for (int r0 = 0; r0 < n_in_rows; r0 += PERIOD) {
 #pragma unroll
-            for (int j = 0; j < PERIOD; ++j) {
-              const int r = r0 + j;
-              if (r < n_in_rows) {
-                u64 v[NIN];
+          for (int oy = 0; oy < RH; ++oy) {
 #pragma unroll
-                for (int kx = 0; kx < NIN; ++kx)
-                  asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v[kx]) : "r"(e_ptr + kx * e_px_bytes));
-                e_ptr += e_row_bytes;
-#pragma unroll
-                for (int ky = 0; ky < KS; ++ky) {
-                  if ((j - ky + PERIOD * KS) % S == 0 && r >= ky && r - ky < out_span) {   // feeds a row this unit owns
-                    const int slot = ((j - ky + PERIOD * KS) / S) % NSLOT;
-#pragma unroll
-                    for (int xx = 0; xx < NX; ++xx)
-#pragma unroll
-                      for (int kx = 0; kx < KS; ++kx)
-                        acc[slot][xx] = ffma2(v[xx * S + kx], wreg[ky * KS + kx], acc[slot][xx]);
-                  }
-                }
-              }
-              if ((j - (KS - 1) + PERIOD * KS) % S == 0) {
-                const int slot_done = ((j - (KS - 1) + PERIOD * KS) / S) % NSLOT;
-                const int num = r - (KS - 1);
-                if (num >= 0 && num < rows_here * S) {             // output row num / S is complete
-                  u64 o[NX];
-#pragma unroll
-                  for (int xx = 0; xx < NX; ++xx) o[xx] = swish2(acc[slot_done][xx]);
-#pragma unroll
-                  for (int xx = 0; xx < NX; ++xx) {
-                    if (x_ok[xx]) {
-                      psum = fadd2(psum, o[xx]);
-                      float a, b;
-                      upk2(o[xx], a, b);
-                      *reinterpret_cast<float2*>(o_ptr + xx * Cexp) = make_float2(a, b);
-                    }
-                  }
-                  o_ptr += o_row;
-                }
-#pragma unroll
-                for (int xx = 0; xx < NX; ++xx) acc[slot_done][xx] = bv2;
+            for (int xx = 0; xx < NX; ++xx) {
+              if (oy < rows_here && c_ok && oxr0 + xx < TW && ox0 + oxr0 + xx < Wo) {
+                psum = fadd2(psum, o[oy][xx]);
+                float a, b;
+                upk2(o[oy][xx], a, b);
+                *reinterpret_cast<float2*>(o_ptr + oy * o_row + xx * Cexp) = make_float2(a, b);
               }
             }
           }
@@ -455,7 +440,10 @@ inline Plan make_plan(const BlockSpec& b) {
   p.tiles_y = (b.hout + p.TH - 1) / p.TH;
   p.tiles_x = (b.wout + p.TW - 1) / p.TW;
   if (((p.TW + p.NX - 1) / p.NX) * p.NYS > MAX_UNITS) return p;
-  p.smem_bytes = 128 + 2 * p.Kp * p.cc * 4 + (p.MT * 128 + E_SLACK_ROWS) * (p.cc + 4) * 4;
+  p.RH = (p.TH + p.NYS - 1) / p.NYS;
+  // the last y segment computes (never stores) rows past the tile when TH is not a multiple of RH
+  const int e_rows = std::max(p.MT * 128, ((p.NYS * p.RH - 1) * b.s + b.k) * p.IW);
+  p.smem_bytes = 128 + 2 * p.Kp * p.cc * 4 + (e_rows + E_SLACK_ROWS) * (p.cc + 4) * 4;
   p.ok = 1;
   return p;
 }
