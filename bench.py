@@ -250,16 +250,23 @@ def main():
 
     from cosypose_b200.rendering import PreRenderedViews
 
+    # device-side landing buffers of the e2e leg are allocated once, as a serving loop would: every step copies
+    # that step's frames, intrinsics, detections and views from pinned host memory into them
+    e_images, e_K, e_boxes = torch.empty_like(d_images), torch.empty_like(d_K), torch.empty_like(d_boxes)
+    e_views = [torch.empty(v.shape, dtype=torch.uint8, device=dev) for v in h_views]
+    e_rv = PreRenderedViews.from_uint8(e_views, BSZ)
+    e_det = tc.PandasTensorCollection(infos=infos, bboxes=e_boxes)
+
     def step_e2e():
-        imgs = h_images.to(dev, non_blocking=True)
-        K = h_K.to(dev, non_blocking=True)
-        boxes = h_boxes.to(dev, non_blocking=True)
-        stages = [v.to(dev, non_blocking=True) for v in h_views]
-        rv = PreRenderedViews.from_uint8(stages, BSZ)
-        pred.coarse_model.renderer = rv
-        pred.refiner_model.renderer = rv
-        det_ = tc.PandasTensorCollection(infos=infos, bboxes=boxes)
-        final, _ = pred.get_predictions(imgs, K, detections=det_, n_coarse_iterations=N_COARSE,
+        e_images.copy_(h_images, non_blocking=True)
+        e_K.copy_(h_K, non_blocking=True)
+        e_boxes.copy_(h_boxes, non_blocking=True)
+        for dst, src in zip(e_views, h_views):
+            dst.copy_(src, non_blocking=True)
+        e_rv.reset()
+        pred.coarse_model.renderer = e_rv
+        pred.refiner_model.renderer = e_rv
+        final, _ = pred.get_predictions(e_images, e_K, detections=e_det, n_coarse_iterations=N_COARSE,
                                         n_refiner_iterations=N_REFINE)
         poses = gather_poses(final.poses) if world > 1 else final.poses
         h_out[:poses.shape[0]].copy_(poses, non_blocking=True)

@@ -97,6 +97,12 @@ static int upload_xdw(PoseModel& m, BlockWeights& w, const float* W_nk, const st
   return 0;
 }
 
+static void clear_graphs(cosyb200_handle* h) {
+  for (auto& e : h->graphs) cudaGraphExecDestroy(e.exec);
+  h->graphs.clear();
+  h->model_epoch += 1;
+}
+
 static void free_model(PoseModel& m) {
   for (void* p : m.allocs) cudaFree(p);
   m = PoseModel();
@@ -525,11 +531,13 @@ int cosyb200_create(cosyb200_handle** out, int device, int max_batch) {
 int cosyb200_destroy(cosyb200_handle* h) {
   if (!h) return COSYB200_OK;
   DeviceGuard guard(h->device);
+  clear_graphs(h);
+  if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
   free_model(h->models[0]);
   free_model(h->models[1]);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   void* ptrs[] = {h->act[0], h->act[1], h->buf_e, h->buf_d, h->pool_partial, h->gate, h->crops, h->pose9,
-                  h->pts_sampled, h->sym, h->n_sym, h->aabb};
+                  h->pts_sampled, h->sym, h->n_sym, h->aabb, h->io_buf};
   for (void* p : ptrs) if (p) cudaFree(p);
   delete h;
   return COSYB200_OK;
@@ -541,6 +549,7 @@ int cosyb200_load_pose_model(cosyb200_handle* h, int slot, int n, const char* co
   CB_CHECK_ARG(slot == 0 || slot == 1, "load_pose_model: slot %d", slot);
   CB_CHECK_ARG(n > 0 && names && ptrs && numels, "load_pose_model: empty state dict");
   DeviceGuard guard(h->device);
+  clear_graphs(h);
   std::map<std::string, std::pair<const float*, int64_t>> sd;
   for (int i = 0; i < n; ++i) sd[names[i]] = {ptrs[i], numels[i]};
   bool ok = true;
@@ -695,6 +704,7 @@ int cosyb200_set_meshes(cosyb200_handle* h, int n_labels, int n_points, const fl
   CB_CHECK_ARG((points == nullptr) || (n_sample == N_SAMPLE && point_ids && n_points >= n_sample),
                "set_meshes: need %d sampled point ids out of >= %d points", N_SAMPLE, N_SAMPLE);
   DeviceGuard guard(h->device);
+  clear_graphs(h);
   // points == NULL replaces the symmetry / AABB tables only: an engine shared with the pose predictors keeps
   // its sampled points (they belong to the same label set)
   CB_CHECK_ARG(points != nullptr || h->pts_sampled == nullptr || n_labels == h->n_labels,
@@ -814,18 +824,105 @@ int cosyb200_refine_n(cosyb200_handle* h, int slot, int B, int n_iter, const flo
                       float* pose9, void* stream) {
   if (int rc = check_batch(h, B, "refine_n")) return rc;
   CB_CHECK_ARG(n_iter >= 1, "refine_n: n_iter %d", n_iter);
-  for (int n = 0; n < n_iter; ++n) {
-    const float* tin = n == 0 ? TCO_in : TCO_out + (size_t)(n - 1) * B * 16;
-    int rc = cosyb200_prepare_iter(h, B, img_h, img_w, K, tin, label_ids, boxes_rend + (size_t)n * B * 4,
-                                   boxes_crop + (size_t)n * B * 4, K_crop + (size_t)n * B * 9, stream);
-    if (rc) return rc;
-    rc = cosyb200_refine_iter(h, slot, B, images, n_images, img_h, img_w, im_ids,
-                              boxes_crop + (size_t)n * B * 4,
-                              (const char*)renders + (size_t)n * B * 3 * RENDER_H * RENDER_W * (render_u8 ? 1 : 4),
-                              render_u8, K_crop + (size_t)n * B * 9, tin, pose9 + (size_t)n * B * POSE_DIM,
-                              TCO_out + (size_t)n * B * 16, stream);
-    if (rc) return rc;
+  struct Io { const int32_t* im_ids; const float* K; const int32_t* label_ids; const float* TCO_in;
+              float *TCO_out, *K_crop, *boxes_rend, *boxes_crop, *pose9; };
+  auto run = [&](void* st, const Io& io) -> int {
+    for (int n = 0; n < n_iter; ++n) {
+      const float* tin = n == 0 ? io.TCO_in : io.TCO_out + (size_t)(n - 1) * B * 16;
+      int rc = cosyb200_prepare_iter(h, B, img_h, img_w, io.K, tin, io.label_ids, io.boxes_rend + (size_t)n * B * 4,
+                                     io.boxes_crop + (size_t)n * B * 4, io.K_crop + (size_t)n * B * 9, st);
+      if (rc) return rc;
+      rc = cosyb200_refine_iter(h, slot, B, images, n_images, img_h, img_w, io.im_ids,
+                                io.boxes_crop + (size_t)n * B * 4,
+                                (const char*)renders + (size_t)n * B * 3 * RENDER_H * RENDER_W * (render_u8 ? 1 : 4),
+                                render_u8, io.K_crop + (size_t)n * B * 9, tin, io.pose9 + (size_t)n * B * POSE_DIM,
+                                io.TCO_out + (size_t)n * B * 16, st);
+      if (rc) return rc;
+    }
+    return COSYB200_OK;
+  };
+  const Io direct{im_ids, K, label_ids, TCO_in, TCO_out, K_crop, boxes_rend, boxes_crop, pose9};
+  const bool graph_ok = h->use_graph && !h->profiling && h->dump_block < 0 && h->trace_block < 0 &&
+                        n_iter <= cosyb200_handle::GRAPH_MAX_ITER;
+  if (!graph_ok) return run(stream, direct);
+
+  // Graph path.  The small per-hypothesis inputs and outputs go through buffers owned by the handle (plain async
+  // copies around the graph launch), so the captured launches only depend on the shape of the call, the frame and
+  // view buffers and the engine options: the graph is replayed whenever those repeat.
+  DeviceGuard guard(h->device);
+  cudaStream_t cst = (cudaStream_t)stream;
+  const size_t Bmax = (size_t)h->max_batch, NI = cosyb200_handle::GRAPH_MAX_ITER;
+  if (!h->io_buf) {
+    // layout (floats): K 9B | TCO_in 16B | im_ids B | label_ids B | TCO_out 16B NI | K_crop 9B NI | boxes_rend 4B NI |
+    //                  boxes_crop 4B NI | pose9 9B NI
+    void* p = nullptr;
+    if (int rc = dev_alloc(&p, Bmax * (9 + 16 + 2 + NI * (16 + 9 + 4 + 4 + POSE_DIM)) * 4)) return rc;
+    h->io_buf = (float*)p;
   }
+  float* b_K = h->io_buf;
+  float* b_TCO = b_K + Bmax * 9;
+  int32_t* b_im = (int32_t*)(b_TCO + Bmax * 16);
+  int32_t* b_lab = b_im + Bmax;
+  float* b_out = (float*)(b_lab + Bmax);
+  float* b_Kc = b_out + Bmax * NI * 16;
+  float* b_br = b_Kc + Bmax * NI * 9;
+  float* b_bc = b_br + Bmax * NI * 4;
+  float* b_p9 = b_bc + Bmax * NI * 4;
+  const Io staged{b_im, b_K, b_lab, b_TCO, b_out, b_Kc, b_br, b_bc, b_p9};
+  const std::vector<uint64_t> key = {
+      (uint64_t)slot, (uint64_t)B, (uint64_t)n_iter, (uint64_t)n_images, (uint64_t)img_h, (uint64_t)img_w,
+      (uint64_t)render_u8, (uint64_t)images, (uint64_t)renders,
+      (uint64_t)h->gemm_impl, (uint64_t)h->xdw, (uint64_t)h->dw_impl, (uint64_t)h->tc_groups, h->model_epoch};
+  cosyb200_handle::RefineGraph* g = nullptr;
+  for (auto& e : h->graphs)
+    if (e.key == key) g = &e;
+  if (!g) {
+    // Callers that hand over fresh frame / view buffers on every call would pay capture + instantiation each time:
+    // after a few misses in a row go back to plain launches and only retry a capture now and then.
+    h->graph_miss_streak += 1;
+    if (h->graph_miss_streak > 3 && h->graph_miss_streak % 16 != 0) return run(stream, direct);
+    if (!h->cap_stream) CB_CUDA(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
+    int64_t before[cosyb200_handle::N_CAT];
+    for (int i = 0; i < cosyb200_handle::N_CAT; ++i) before[i] = h->launches[i];
+    CB_CUDA(cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeRelaxed));
+    const int rc = run(h->cap_stream, staged);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(h->cap_stream, &graph);
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (ce != cudaSuccess) { set_error("refine_n: stream capture failed: %s", cudaGetErrorString(ce)); return COSYB200_ECUDA; }
+    cosyb200_handle::RefineGraph e;
+    e.key = key;
+    const cudaError_t ie = cudaGraphInstantiate(&e.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess) { set_error("refine_n: cudaGraphInstantiate: %s", cudaGetErrorString(ie)); return COSYB200_ECUDA; }
+    for (int i = 0; i < cosyb200_handle::N_CAT; ++i) {
+      e.launches[i] = h->launches[i] - before[i];
+      h->launches[i] = before[i];
+    }
+    if (h->graphs.size() >= 16) {            // evict the least recently used entry
+      size_t lru = 0;
+      for (size_t i = 1; i < h->graphs.size(); ++i)
+        if (h->graphs[i].last_use < h->graphs[lru].last_use) lru = i;
+      cudaGraphExecDestroy(h->graphs[lru].exec);
+      h->graphs.erase(h->graphs.begin() + lru);
+    }
+    h->graphs.push_back(e);
+    g = &h->graphs.back();
+  }
+  else h->graph_miss_streak = 0;
+  g->last_use = ++h->graph_clock;
+  const size_t nb = (size_t)n_iter * B;
+  CB_CUDA(cudaMemcpyAsync(b_K, K, (size_t)B * 9 * 4, cudaMemcpyDeviceToDevice, cst));
+  CB_CUDA(cudaMemcpyAsync(b_TCO, TCO_in, (size_t)B * 16 * 4, cudaMemcpyDeviceToDevice, cst));
+  CB_CUDA(cudaMemcpyAsync(b_im, im_ids, (size_t)B * 4, cudaMemcpyDeviceToDevice, cst));
+  CB_CUDA(cudaMemcpyAsync(b_lab, label_ids, (size_t)B * 4, cudaMemcpyDeviceToDevice, cst));
+  CB_CUDA(cudaGraphLaunch(g->exec, cst));
+  CB_CUDA(cudaMemcpyAsync(TCO_out, b_out, nb * 16 * 4, cudaMemcpyDeviceToDevice, cst));
+  CB_CUDA(cudaMemcpyAsync(K_crop, b_Kc, nb * 9 * 4, cudaMemcpyDeviceToDevice, cst));
+  CB_CUDA(cudaMemcpyAsync(boxes_rend, b_br, nb * 4 * 4, cudaMemcpyDeviceToDevice, cst));
+  CB_CUDA(cudaMemcpyAsync(boxes_crop, b_bc, nb * 4 * 4, cudaMemcpyDeviceToDevice, cst));
+  CB_CUDA(cudaMemcpyAsync(pose9, b_p9, nb * POSE_DIM * 4, cudaMemcpyDeviceToDevice, cst));
+  for (int i = 0; i < cosyb200_handle::N_CAT; ++i) h->launches[i] += g->launches[i];
   return COSYB200_OK;
 }
 
@@ -839,6 +936,11 @@ int cosyb200_set_option(cosyb200_handle* h, const char* name, int value) {
   if (strcmp(name, "tc_groups") == 0) {
     CB_CHECK_ARG(value >= 0 && value <= 2, "set_option: tc_groups must be 0 (per layer), 1 or 2");
     h->tc_groups = value;
+    return COSYB200_OK;
+  }
+  if (strcmp(name, "graph") == 0) {
+    CB_CHECK_ARG(value == 0 || value == 1, "set_option: graph must be 0 (plain launches) or 1 (refine_n replays CUDA graphs)");
+    h->use_graph = value;
     return COSYB200_OK;
   }
   if (strcmp(name, "xdw") == 0) {

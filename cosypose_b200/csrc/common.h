@@ -120,6 +120,21 @@ struct cosyb200_handle {
   std::vector<int> ev_blk;
   bool profiling = false;
   int tc_groups = 0;   // 3xTF32 kernel: 0 = pick the producer-group variant per layer, 1 / 2 = force it
+  // CUDA graphs of cosyb200_refine_n, keyed by every argument that is baked into the captured launches
+  struct RefineGraph {
+    std::vector<uint64_t> key;
+    cudaGraphExec_t exec = nullptr;
+    int64_t launches[N_CAT] = {0};
+    uint64_t last_use = 0;
+  };
+  std::vector<RefineGraph> graphs;
+  static constexpr int GRAPH_MAX_ITER = 8;
+  float* io_buf = nullptr;             // staging of the small per-hypothesis inputs / outputs of the graph path
+  uint64_t graph_clock = 0;
+  int graph_miss_streak = 0;
+  uint64_t model_epoch = 0;            // bumped whenever weights or mesh tables are (re)loaded: invalidates the graphs
+  cudaStream_t cap_stream = nullptr;   // capture happens here (the caller's stream may be the legacy stream)
+  int use_graph = 1;      // 1: refine_n replays a captured graph when its arguments repeat
   int trace_block = -1;   // debugging: the fused kernel of this block stamps its phases into the debug trace buffer
   int xdw = 1;         // 1: blocks with a kernels_xdw.cuh plan run expand + depthwise + pooling fused
   int dw_impl = 1;     // depthwise of the small-spatial blocks: 0 = rolling window + k_se_gate, 1 = k_dw_tile + k_se_fc2
