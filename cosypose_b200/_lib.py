@@ -5,7 +5,7 @@ product raises.  Build it with `python -c "import __graft_entry__ as g; g.build(
 `make -C cosypose_b200/csrc`.
 """
 import ctypes
-from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_void_p
 from pathlib import Path
 
 import os
@@ -40,6 +40,10 @@ _SIGS = {
     'cosyb200_refine_n': ([_P, c_int, c_int, c_int, _P, c_int, c_int, c_int, _P, _P, _P, _P, c_int, _P,
                            _P, _P, _P, _P, _P, _P], c_int),
     'cosyb200_set_option': ([_P, c_char_p, c_int], c_int),
+    'cosyb200_nccl_unique_id': ([_P], c_int),
+    'cosyb200_nccl_comm_init': ([_P, c_int, c_int, _P], c_int),
+    'cosyb200_nccl_comm_destroy': ([_P], c_int),
+    'cosyb200_allgather_candidates': ([_P, _P, _P, c_int64, _P], c_int),
     'cosyb200_debug_pointwise': ([_P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, c_int, _P, c_int, _P, _P], c_int),
     'cosyb200_debug_trace': ([_P, _P], c_int),
     'cosyb200_debug_dump': ([_P, c_int, _P, _P, _P], c_int),
@@ -53,6 +57,9 @@ _SIGS = {
     'cosyb200_compose_inv': ([_P, c_int64, _P, _P, _P, _P, _P, _P], c_int),
     'cosyb200_ba_linearize': ([_P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, c_float,
                                _P, _P, _P, _P, _P, _P, _P, _P], c_int),
+    'cosyb200_ba_linearize_f64': ([_P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, c_float,
+                                   _P, _P, _P, _P, _P, _P], c_int),
+    'cosyb200_lm_solve': ([_P, c_int, _P, _P, c_double, _P, _P, _P], c_int),
     'cosyb200_ransac_inliers': ([c_int64, _P, _P, c_int64, _P, _P, _P, _P, c_float, c_int, _P, _P,
                                  POINTER(c_int64), _P, POINTER(c_int64)], c_int),
     'cosyb200_scatter_argmin': ([c_int64, _P, _P, c_int64, _P], c_int),

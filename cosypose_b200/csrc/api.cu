@@ -4,6 +4,8 @@
 #include <map>
 #include <string>
 
+#include <dlfcn.h>
+
 #include "common.h"
 #include "effnet_table.h"
 #include "kernels_backbone.cuh"
@@ -96,6 +98,47 @@ static int upload_xdw(PoseModel& m, BlockWeights& w, const float* W_nk, const st
   w.expand_x_inv = 1.0f / sc;
   return 0;
 }
+
+// ---- multi-GPU exchange: NCCL bound at run time ---------------------------------------------------
+namespace {
+struct NcclId { char b[128]; };   // ncclUniqueId (passed by value)
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+int nccl_bind() {
+  if (g_nccl.lib) return 0;
+  void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);   // the copy already loaded (PyTorch's), if any
+  if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW);
+  if (!lib) lib = dlopen("libnccl.so", RTLD_NOW);
+  if (!lib) { set_error("NCCL is not available: %s", dlerror()); return COSYB200_ESTATE; }
+  g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+  g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(lib, "ncclCommInitRank");
+  g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(lib, "ncclCommDestroy");
+  g_nccl.AllGather = (decltype(g_nccl.AllGather))dlsym(lib, "ncclAllGather");
+  g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(lib, "ncclGetErrorString");
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.AllGather) {
+    set_error("NCCL symbols missing in the loaded libnccl");
+    return COSYB200_ESTATE;
+  }
+  g_nccl.lib = lib;
+  return 0;
+}
+#define CB_NCCL(expr)                                                                             \
+  do {                                                                                            \
+    const int r_ = (expr);                                                                        \
+    if (r_ != 0) {                                                                                \
+      set_error("%s -> %s", #expr, g_nccl.GetErrorString ? g_nccl.GetErrorString(r_) : "nccl error"); \
+      return COSYB200_ECUDA;                                                                      \
+    }                                                                                             \
+  } while (0)
+}  // namespace
+
 
 static void clear_graphs(cosyb200_handle* h) {
   for (auto& e : h->graphs) cudaGraphExecDestroy(e.exec);
@@ -532,12 +575,13 @@ int cosyb200_destroy(cosyb200_handle* h) {
   if (!h) return COSYB200_OK;
   DeviceGuard guard(h->device);
   clear_graphs(h);
+  if (h->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->nccl_comm);
   if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
   free_model(h->models[0]);
   free_model(h->models[1]);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   void* ptrs[] = {h->act[0], h->act[1], h->buf_e, h->buf_d, h->pool_partial, h->gate, h->crops, h->pose9,
-                  h->pts_sampled, h->sym, h->n_sym, h->aabb, h->io_buf};
+                  h->pts_sampled, h->sym, h->n_sym, h->aabb, h->io_buf, h->ba_ws, h->lm_ws};
   for (void* p : ptrs) if (p) cudaFree(p);
   delete h;
   return COSYB200_OK;
@@ -1020,6 +1064,47 @@ int cosyb200_debug_trace(cosyb200_handle* h, long long* trace_dev) {
   return COSYB200_OK;
 }
 
+// ---- multi-GPU exchange ---------------------------------------------------------------------------
+int cosyb200_nccl_unique_id(char* id128_host) {
+  CB_CHECK_ARG(id128_host != nullptr, "nccl_unique_id: null pointer");
+  if (int rc = nccl_bind()) return rc;
+  CB_NCCL(g_nccl.GetUniqueId(id128_host));
+  return COSYB200_OK;
+}
+
+int cosyb200_nccl_comm_init(cosyb200_handle* h, int world, int rank, const char* id128_host) {
+  CB_CHECK_ARG(h != nullptr && id128_host != nullptr && world >= 1 && rank >= 0 && rank < world, "nccl_comm_init: bad arguments");
+  if (int rc = nccl_bind()) return rc;
+  DeviceGuard guard(h->device);
+  if (h->nccl_comm) { g_nccl.CommDestroy(h->nccl_comm); h->nccl_comm = nullptr; }
+  NcclId id;
+  memcpy(id.b, id128_host, 128);
+  CB_NCCL(g_nccl.CommInitRank(&h->nccl_comm, world, id, rank));
+  h->nccl_world = world;
+  h->nccl_rank = rank;
+  return COSYB200_OK;
+}
+
+int cosyb200_nccl_comm_destroy(cosyb200_handle* h) {
+  CB_CHECK_ARG(h != nullptr, "nccl_comm_destroy: null handle");
+  if (h->nccl_comm) {
+    DeviceGuard guard(h->device);
+    g_nccl.CommDestroy(h->nccl_comm);
+    h->nccl_comm = nullptr;
+  }
+  return COSYB200_OK;
+}
+
+int cosyb200_allgather_candidates(cosyb200_handle* h, const float* local_dev, float* all_dev,
+                                  int64_t count_per_rank, void* stream) {
+  CB_CHECK_ARG(h != nullptr && all_dev != nullptr && count_per_rank >= 0, "allgather_candidates: bad arguments");
+  if (!h->nccl_comm) { set_error("allgather_candidates: call cosyb200_nccl_comm_init first"); return COSYB200_ESTATE; }
+  DeviceGuard guard(h->device);
+  const float* send = local_dev ? local_dev : all_dev + (size_t)h->nccl_rank * count_per_rank;   // in place
+  CB_NCCL(g_nccl.AllGather(send, all_dev, (size_t)count_per_rank, /* ncclFloat32 */ 7, h->nccl_comm, (cudaStream_t)stream));
+  return COSYB200_OK;
+}
+
 // ---- launch accounting ------------------------------------------------------------------------
 int cosyb200_profile_enable(cosyb200_handle* h, int on) {
   CB_CHECK_ARG(h != nullptr, "profile_enable: null handle");
@@ -1165,6 +1250,74 @@ int cosyb200_ba_linearize(cosyb200_handle* h, int n_cand, int n_obj, int n_view,
     k_ba_normal<<<grid, block, 0, st>>>(n_cand, n_pts, n_obj, n_view, cand_obj, cand_view, Jc, errors, JtJ, Jte);
     CB_LAUNCH_CHECK();
   }
+  return COSYB200_OK;
+}
+
+// float64 evaluation of the same linearisation (see kernels_ba.cuh): JtJ64 [n_params^2], Jte64 [n_params], loss64 [1]
+int cosyb200_ba_linearize_f64(cosyb200_handle* h, int n_cand, int n_obj, int n_view, int n_pts,
+                              const float* cand_TCO, const int32_t* cand_obj, const int32_t* cand_view,
+                              const int32_t* cand_label, const float* TWO_9d, const float* TCW_9d,
+                              const float* K, const float* points, float residuals_threshold,
+                              float* align_dists, float* aligned, double* JtJ64, double* Jte64, double* loss64,
+                              void* stream) {
+  CB_CHECK_ARG(h != nullptr && n_cand >= 1 && n_obj >= 1 && n_view >= 1 && n_pts >= 1, "ba_linearize_f64: bad sizes");
+  CB_CHECK_ARG(cand_TCO && cand_obj && cand_view && cand_label && TWO_9d && TCW_9d && K && points,
+               "ba_linearize_f64: null input");
+  CB_CHECK_ARG(align_dists && aligned && loss64, "ba_linearize_f64: null output");
+  if (!h->sym) { set_error("ba_linearize_f64: meshes not set"); return COSYB200_ESTATE; }
+  DeviceGuard guard(h->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t n_res = (size_t)n_cand * n_pts * 2;
+  const size_t need = n_res * 19;
+  if (h->ba_ws_elems < need) {
+    if (h->ba_ws) { CB_CUDA(cudaStreamSynchronize(st)); cudaFree(h->ba_ws); h->ba_ws = nullptr; }
+    CB_CUDA(cudaMalloc((void**)&h->ba_ws, need * 8));
+    h->ba_ws_elems = need;
+  }
+  double* err64 = h->ba_ws;
+  double* Jc64 = h->ba_ws + n_res;
+  {
+    LaunchScope ls(h, CAT_RANSAC, st);
+    k_ba_align<<<(n_cand + 63) / 64, 64, 0, st>>>(n_cand, n_pts, cand_TCO, cand_obj, cand_view, cand_label, TWO_9d,
+                                                  TCW_9d, K, points, h->sym, h->n_sym, h->s_max, align_dists, aligned);
+  }
+  CB_LAUNCH_CHECK();
+  {
+    LaunchScope ls(h, CAT_RANSAC, st);
+    k_ba_residuals_d<<<(n_cand * n_pts + 63) / 64, 64, 0, st>>>(n_cand, n_pts, aligned, cand_obj, cand_view, cand_label,
+                                                                TWO_9d, TCW_9d, K, points, err64, Jc64);
+  }
+  CB_LAUNCH_CHECK();
+  {
+    LaunchScope ls(h, CAT_RANSAC, st);
+    k_ba_loss_d<<<1, 256, 0, st>>>((int)n_res, err64, (double)residuals_threshold, loss64);
+  }
+  CB_LAUNCH_CHECK();
+  if (JtJ64 && Jte64) {
+    const int n_params = 9 * (n_obj + n_view);
+    dim3 block(32, 8), grid((n_params + 1 + 31) / 32, (n_params + 7) / 8);
+    LaunchScope ls(h, CAT_RANSAC, st);
+    k_ba_normal_d<<<grid, block, 0, st>>>(n_cand, n_pts, n_obj, n_view, cand_obj, cand_view, Jc64, err64, JtJ64, Jte64);
+    CB_LAUNCH_CHECK();
+  }
+  return COSYB200_OK;
+}
+
+// step [n] = (JtJ64 + lambda I)^-1 Jte64 on the device (float64 Cholesky, one CTA); n_bad_pivots_dev may be NULL
+int cosyb200_lm_solve(cosyb200_handle* h, int n, const double* JtJ64, const double* Jte64, double lambda,
+                      float* step, int32_t* n_bad_pivots_dev, void* stream) {
+  CB_CHECK_ARG(h != nullptr && n >= 1 && n <= LM_MAX_N && JtJ64 && Jte64 && step, "lm_solve: bad arguments (n <= %d)", LM_MAX_N);
+  DeviceGuard guard(h->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t need = (size_t)n * n;
+  if (h->lm_ws_elems < need) {
+    if (h->lm_ws) { CB_CUDA(cudaStreamSynchronize(st)); cudaFree(h->lm_ws); h->lm_ws = nullptr; }
+    CB_CUDA(cudaMalloc((void**)&h->lm_ws, need * 8));
+    h->lm_ws_elems = need;
+  }
+  LaunchScope ls(h, CAT_RANSAC, st);
+  k_lm_solve<<<1, LM_THREADS, 0, st>>>(n, JtJ64, Jte64, lambda, h->lm_ws, step, n_bad_pivots_dev);
+  CB_LAUNCH_CHECK();
   return COSYB200_OK;
 }
 

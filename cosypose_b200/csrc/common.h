@@ -134,6 +134,10 @@ struct cosyb200_handle {
   int graph_miss_streak = 0;
   uint64_t model_epoch = 0;            // bumped whenever weights or mesh tables are (re)loaded: invalidates the graphs
   cudaStream_t cap_stream = nullptr;   // capture happens here (the caller's stream may be the legacy stream)
+  double* ba_ws = nullptr; size_t ba_ws_elems = 0;   // float64 residuals + compact Jacobian of ba_linearize_f64
+  double* lm_ws = nullptr; size_t lm_ws_elems = 0;   // Cholesky workspace of lm_solve
+  void* nccl_comm = nullptr;   // ncclComm_t created by cosyb200_nccl_comm_init
+  int nccl_world = 1, nccl_rank = 0;
   int use_graph = 1;      // 1: refine_n replays a captured graph when its arguments repeat
   int trace_block = -1;   // debugging: the fused kernel of this block stamps its phases into the debug trace buffer
   int xdw = 1;         // 1: blocks with a kernels_xdw.cuh plan run expand + depthwise + pooling fused

@@ -206,6 +206,38 @@ class Engine:
             _ptr(out['boxes_crop']), _ptr(out['pose']), self._stream()), 'refine_n')
         return out
 
+    # -- multi-GPU exchange --------------------------------------------------------------------
+    def nccl_init(self):
+        """Creates the engine's own NCCL communicator over the ranks of the initialised torch.distributed
+        group (the 128-byte unique id travels through that group's object broadcast)."""
+        import ctypes
+        import torch.distributed as dist
+        rank, world = dist.get_rank(), dist.get_world_size()
+        buf = ctypes.create_string_buffer(128)
+        if rank == 0:
+            _lib.check(self._L.cosyb200_nccl_unique_id(buf), 'nccl_unique_id')
+        box = [bytes(buf.raw)]
+        dist.broadcast_object_list(box, src=0)
+        idbuf = ctypes.create_string_buffer(box[0], 128)
+        _lib.check(self._L.cosyb200_nccl_comm_init(self._h, world, rank, idbuf), 'nccl_comm_init')
+        self.nccl_ready = True
+
+    def allgather_candidates(self, all_records, local=None):
+        """all_records [world * per, rec] float32: every rank's `per` rows are exchanged with one ncclAllGather on
+        the current stream; local=None means this rank's rows are already in place (rows rank*per ...)."""
+        assert getattr(self, 'nccl_ready', False), 'call nccl_init() first'
+        self._chk(all_records, torch.float32, name='all_records')
+        import torch.distributed as dist
+        world = dist.get_world_size()
+        assert all_records.shape[0] % world == 0
+        count = all_records.numel() // world
+        if local is not None:
+            self._chk(local, torch.float32, name='local')
+            assert local.numel() == count
+        _lib.check(self._L.cosyb200_allgather_candidates(self._h, _ptr(local), _ptr(all_records), count,
+                                                         self._stream()), 'allgather_candidates')
+        return all_records
+
     def set_option(self, name, value):
         _lib.check(self._L.cosyb200_set_option(self._h, name.encode(), int(value)), 'set_option')
 
@@ -314,6 +346,39 @@ class Engine:
             _ptr(out['align_dists']), _ptr(out['aligned']), _ptr(out['errors']), _ptr(out['Jc']),
             _ptr(out['JtJ']), _ptr(out['Jte']), _ptr(out['loss']), self._stream()), 'ba_linearize')
         return out
+
+    def ba_linearize_f64(self, cand_TCO, cand_obj, cand_view, cand_label, TWO_9d, TCW_9d, K, points,
+                         residuals_threshold=25.0, normal_equations=True):
+        """ba_linearize evaluated in float64 on the device: JtJ / Jte / loss are float64 device tensors."""
+        n_cand, n_obj, n_view, n_pts = cand_TCO.shape[0], TWO_9d.shape[0], TCW_9d.shape[0], points.shape[1]
+        self._chk(cand_TCO, torch.float32, (n_cand, 4, 4), 'cand_TCO')
+        for t, nm in ((cand_obj, 'cand_obj'), (cand_view, 'cand_view'), (cand_label, 'cand_label')):
+            self._chk(t, torch.int32, (n_cand,), nm)
+        self._chk(TWO_9d, torch.float32, (n_obj, 9), 'TWO_9d')
+        self._chk(TCW_9d, torch.float32, (n_view, 9), 'TCW_9d')
+        self._chk(K, torch.float32, (n_view, 3, 3), 'K')
+        self._chk(points, torch.float32, (points.shape[0], n_pts, 3), 'points')
+        n_params = 9 * (n_obj + n_view)
+        out = dict(align_dists=self._new(n_cand), aligned=self._new(n_cand, 4, 4),
+                   loss=self._new(1, dtype=torch.float64),
+                   JtJ=self._new(n_params, n_params, dtype=torch.float64) if normal_equations else None,
+                   Jte=self._new(n_params, dtype=torch.float64) if normal_equations else None)
+        _lib.check(self._L.cosyb200_ba_linearize_f64(
+            self._h, n_cand, n_obj, n_view, n_pts, _ptr(cand_TCO), _ptr(cand_obj), _ptr(cand_view),
+            _ptr(cand_label), _ptr(TWO_9d), _ptr(TCW_9d), _ptr(K), _ptr(points), float(residuals_threshold),
+            _ptr(out['align_dists']), _ptr(out['aligned']), _ptr(out['JtJ']), _ptr(out['Jte']), _ptr(out['loss']),
+            self._stream()), 'ba_linearize_f64')
+        return out
+
+    def lm_solve(self, JtJ64, Jte64, lambd):
+        """(JtJ + lambda I)^-1 Jte on the device (float64 Cholesky); returns the fp32 step [n]."""
+        n = Jte64.shape[0]
+        self._chk(JtJ64, torch.float64, (n, n), 'JtJ')
+        self._chk(Jte64, torch.float64, (n,), 'Jte')
+        step = self._new(n)
+        _lib.check(self._L.cosyb200_lm_solve(self._h, n, _ptr(JtJ64), _ptr(Jte64), float(lambd), _ptr(step),
+                                             c_void_p(None), self._stream()), 'lm_solve')
+        return step
 
 
 # -- host-side tables ----------------------------------------------------------------------------

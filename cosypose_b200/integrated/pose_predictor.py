@@ -54,7 +54,14 @@ class CoarseRefinePosePredictor:
         return tc.PandasTensorCollection(infos=detections.infos, poses=TCO_init)
 
     def get_predictions(self, images, K, detections=None, data_TCO_init=None,
-                        n_coarse_iterations=1, n_refiner_iterations=1):
+                        n_coarse_iterations=1, n_refiner_iterations=1, shard=False):
+        """shard=True (torch.distributed initialised, one process per GPU): every rank passes the SAME global
+        detections / initial poses, refines the contiguous shard `sharding.shard_bounds` gives it and the per-iteration
+        records of all ranks are exchanged with ONE all-gather, so every rank returns the full result (what the
+        multiview matching stage needs).  Hypotheses are independent, so the result equals the 1-GPU result."""
+        if shard:
+            return self._get_predictions_sharded(images, K, detections, data_TCO_init, n_coarse_iterations,
+                                                 n_refiner_iterations)
         preds = dict()
         if data_TCO_init is None:
             assert detections is not None
@@ -79,3 +86,35 @@ class CoarseRefinePosePredictor:
                 preds[f'refiner/iteration={n}'] = refiner_preds[f'iteration={n}']
             data_TCO = refiner_preds[f'iteration={n_refiner_iterations}']
         return data_TCO, preds
+
+    def _get_predictions_sharded(self, images, K, detections, data_TCO_init, n_coarse_iterations, n_refiner_iterations):
+        from .. import sharding
+        rank, ws = sharding.world()
+        full = detections if data_TCO_init is None else data_TCO_init
+        assert full is not None
+        n = len(full)
+        start, stop = sharding.shard_bounds(n, rank, ws)
+        ids = np.arange(start, stop)
+        model = self.coarse_model or self.refiner_model
+        engine = getattr(model, 'engine', None)
+        if len(ids):
+            local = full[ids]
+            local.infos = local.infos.reset_index(drop=True)
+            kw = dict(detections=local) if data_TCO_init is None else dict(data_TCO_init=local)
+            _, preds_local = self.get_predictions(images, K, n_coarse_iterations=n_coarse_iterations,
+                                                  n_refiner_iterations=n_refiner_iterations, **kw)
+            keys = list(preds_local.keys())
+            records = sharding.pack_records([preds_local[k] for k in keys])
+        else:   # more ranks than hypotheses: this rank contributes padding only
+            keys = ([f'coarse/iteration={i}' for i in range(1, n_coarse_iterations + 1)] if data_TCO_init is None
+                    else ['external_coarse']) + [f'refiner/iteration={i}' for i in range(1, n_refiner_iterations + 1)]
+            device = engine.device if engine is not None else K.device
+            records = torch.zeros((0, len(keys) * sharding.RECORD_FLOATS), dtype=torch.float32, device=device)
+        gathered = sharding.gather_records(records, n, engine=engine)
+        preds = dict()
+        for k, fields in zip(keys, sharding.unpack_records(gathered, len(keys))):
+            if k == 'external_coarse':
+                preds[k] = data_TCO_init
+                continue
+            preds[k] = tc.PandasTensorCollection(full.infos, **fields)
+        return preds[keys[-1]], preds

@@ -148,10 +148,12 @@ class MultiviewRefinement:
         return TWO, TWC
 
     def _linearize(self, TWO_9d, TCW_9d, residuals_threshold=25.0, normal_equations=True):
-        return self.engine.ba_linearize(self.cand_TCO, self._d_obj, self._d_view, self._d_label,
-                                        TWO_9d, TCW_9d, self.K, self.points,
-                                        residuals_threshold=residuals_threshold,
-                                        normal_equations=normal_equations)
+        """Residuals, analytic Jacobian, J^T J, J^T e and the loss in float64 on the device (the reference
+        differentiates fp32 residuals with autograd, :175-214, and is itself ~1e-4 from its float64 evaluation)."""
+        return self.engine.ba_linearize_f64(self.cand_TCO, self._d_obj, self._d_view, self._d_label,
+                                            TWO_9d, TCW_9d, self.K, self.points,
+                                            residuals_threshold=residuals_threshold,
+                                            normal_equations=normal_equations)
 
     def align_TCO_cand(self, TWO_9d, TCW_9d):
         out = self._linearize(TWO_9d, TCW_9d, normal_equations=False)
@@ -171,8 +173,9 @@ class MultiviewRefinement:
 
     # -- Levenberg-Marquardt (reference: :216-278) -----------------------------------------------
     def compute_lm_step(self, JtJ, Jte, lambd):
-        A = JtJ.cpu() + lambd * torch.eye(JtJ.shape[0])
-        return (torch.pinverse(A) @ Jte.cpu()[:, None]).flatten().to(self.device)
+        """h = (JtJ + lambda I)^-1 Jte: the reference's `pinverse` on the CPU (:216-222) of a positive definite matrix,
+        here a float64 Cholesky solve on the device (cosyb200_lm_solve)."""
+        return self.engine.lm_solve(JtJ, Jte, lambd)
 
     def optimize_lm(self, TWO_9d, TCW_9d, optimize_cameras=True, n_iterations=50, residuals_threshold=25,
                     lambd0=1e-3, L_down=9, L_up=11, eps=1e-5):

@@ -35,6 +35,17 @@ class PreRenderedViews:
         self.reset()
         return self
 
+    @classmethod
+    def from_chunks(cls, chunks, bsz_objects=64):
+        """chunks: per (stage, chunk) stacks [n_iter, Bc, ...] in call order, used in place (no copy): a caller
+        that refills the same device buffers every step keeps the engine's captured graphs valid."""
+        self = cls.__new__(cls)
+        self.bsz = bsz_objects
+        self.chunks = [c for c in chunks]
+        assert all(c.is_contiguous() for c in self.chunks)
+        self.reset()
+        return self
+
     def reset(self):
         self._chunk = 0
         self._it = 0

@@ -253,6 +253,41 @@ int cosyb200_ba_linearize(cosyb200_handle* h, int n_cand, int n_obj, int n_view,
                           float* aligned_dev, float* errors_dev, float* Jc_dev, float* JtJ_dev,
                           float* Jte_dev, float* loss_dev, void* stream);
 
+/* The same linearisation evaluated in float64 on the device (residuals, Jacobian, normal equations, loss): the LM
+ * normal equations are ill conditioned in fp32 - the reference's own fp32 result is ~1e-4 from the same code run in
+ * float64 - and the problem is tiny.  Parameters and the aligned poses stay fp32; JtJ64 [n_params^2], Jte64
+ * [n_params] (both may be NULL), loss64 [1] are float64 device buffers of the caller. */
+int cosyb200_ba_linearize_f64(cosyb200_handle* h, int n_cand, int n_obj, int n_view, int n_pts,
+                              const float* cand_TCO_dev, const int32_t* cand_obj_dev,
+                              const int32_t* cand_view_dev, const int32_t* cand_label_dev,
+                              const float* TWO_9d_dev, const float* TCW_9d_dev, const float* K_dev,
+                              const float* points_dev, float residuals_threshold, float* align_dists_dev,
+                              float* aligned_dev, double* JtJ64_dev, double* Jte64_dev, double* loss64_dev,
+                              void* stream);
+
+/* compute_lm_step (reference: multiview/bundle_adjustment.py:216-222, `pinverse(JtJ + lambda I) @ Jte` on the CPU):
+ * float64 Cholesky solve on the device, one CTA; step_dev [n] fp32.  n_bad_pivots_dev (may be NULL) receives the
+ * number of non-positive pivots that had to be replaced (0 for a positive definite system). */
+int cosyb200_lm_solve(cosyb200_handle* h, int n, const double* JtJ64_dev, const double* Jte64_dev, double lambda,
+                      float* step_dev, int32_t* n_bad_pivots_dev, void* stream);
+
+/* ---- multi-GPU exchange ----------------------------------------------------------
+ * Hypotheses shard across ranks with no data-path collective; the ONE exchange is an all-gather of fixed-size fp32
+ * records per hypothesis after the last refinement iteration.  The reference gathers per-rank predictions through
+ * pickle files on a shared filesystem (utils/tensor_collection.py:142-163, datasets/samplers.py:20-34).
+ * NCCL is bound at run time (dlopen of the libnccl already in the process, e.g. PyTorch's), so the library loads
+ * and every other entry point works on hosts without NCCL.
+ *   cosyb200_nccl_unique_id   rank 0 creates the 128-byte id; the caller broadcasts it (any transport)
+ *   cosyb200_nccl_comm_init   every rank: communicator of `world` ranks for the handle's device
+ *   cosyb200_allgather_candidates   all_dev [world * count_per_rank] floats; rank r's records live at
+ *       all_dev + r * count_per_rank.  local_dev == NULL means "already there" (in-place: pass the shard's slice of
+ *       all_dev as the output buffer of cosyb200_refine_n and nothing is staged); enqueued on `stream`. */
+int cosyb200_nccl_unique_id(char* id128_host);
+int cosyb200_nccl_comm_init(cosyb200_handle* h, int world, int rank, const char* id128_host);
+int cosyb200_nccl_comm_destroy(cosyb200_handle* h);
+int cosyb200_allgather_candidates(cosyb200_handle* h, const float* local_dev, float* all_dev,
+                                  int64_t count_per_rank, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -16,6 +16,7 @@ import torch
 HERE = Path(__file__).resolve().parent
 sys.path.insert(0, str(HERE.parents[1]))
 sys.path.insert(0, str(HERE))
+sys.path.insert(0, str(HERE.parents[1] / "baseline"))
 
 import ref_harness  # noqa: E402
 from cosypose_b200 import synthetic as syn  # noqa: E402

@@ -127,10 +127,42 @@ def test_ba_linearize_vs_autograd_oracle():
         assert (rows[r] - dense).abs().max() < 1e-4 * dense.abs().max().clamp_min(1.0)
 
 
+def test_ba_linearize_f64_and_lm_solve():
+    """float64 linearisation on the device against the autograd oracle evaluated in float64 (1e-9 relative), and the
+    device Cholesky solve against numpy's float64 solve of the same damped system."""
+    from oracle import multiview_oracle as mo
+    sc = Scene(3, 4, 5, (1, 2), True, 1)
+    eng, mesh_db = _engine(sc)
+    dev = eng.device
+    uniq = np.unique(sc.label_ids)
+    cand_obj = np.searchsorted(uniq, sc.label_ids).astype(np.int32)
+    gen = torch.Generator().manual_seed(0)
+    TWO_9d = mo.extract_pose9d(sc.TWO[:len(uniq)]) + 0.01 * torch.randn((len(uniq), 9), generator=gen)
+    TCW_9d = mo.extract_pose9d(mo.invert_T(sc.TWC)) + 0.01 * torch.randn((sc.n_views, 9), generator=gen)
+    d = lambda t: t.double()
+    e_ref, loss_ref, J_ref, _ = mo.ba_linearize(d(sc.poses), cand_obj, sc.view_ids, sc.label_ids, d(TWO_9d), d(TCW_9d),
+                                                d(sc.K), d(sc.aabb), d(sc.sym), sc.n_sym)
+    assert J_ref.dtype == torch.float64
+    i32 = lambda a: torch.as_tensor(np.asarray(a), dtype=torch.int32, device=dev)
+    out = eng.ba_linearize_f64(sc.poses.to(dev).contiguous(), i32(cand_obj), i32(sc.view_ids), i32(sc.label_ids),
+                               TWO_9d.to(dev), TCW_9d.to(dev), sc.K.to(dev), sc.aabb.to(dev).contiguous())
+    JtJ_ref, Jte_ref = J_ref.t() @ J_ref, J_ref.t() @ e_ref
+    assert out['JtJ'].dtype == torch.float64
+    # the aligned candidate poses are fp32 data (cand_TCO @ S), everything after them is float64
+    assert (out['JtJ'].cpu() - JtJ_ref).abs().max() < 1e-9 * JtJ_ref.abs().max()
+    assert (out['Jte'].cpu() - Jte_ref).abs().max() < 1e-5 * Jte_ref.abs().max().clamp_min(1.0)
+    assert abs(out['loss'].item() - loss_ref.item()) < 1e-5 * max(1.0, loss_ref.item())
+    for lambd in (1e-3, 1e-7):
+        h = eng.lm_solve(out['JtJ'], out['Jte'], lambd).cpu().double().numpy()
+        A = out['JtJ'].cpu().numpy() + lambd * np.eye(JtJ_ref.shape[0])
+        h_ref = np.linalg.solve(A, out['Jte'].cpu().numpy())
+        assert np.abs(h - h_ref).max() < 1e-6 * max(1.0, np.abs(h_ref).max()), (lambd, np.abs(h - h_ref).max())
+
+
 @pytest.mark.parametrize('name', ['scene_state_small', 'scene_state_sym'])
 def test_predict_scene_state_vs_reference(golden_dir, name):
     """MultiviewScenePredictor.predict_scene_state end to end (matching + view groups + LM bundle
-    adjustment + reprojection).  LM in fp32 with different Jacobian arithmetic: poses within 1e-3."""
+    adjustment + reprojection): integer outputs bit-exact, gauge-invariant poses within 1e-4 of the reference."""
     from cosypose_b200.integrated.multiview_predictor import MultiviewScenePredictor
     g = np.load(golden_dir / f'{name}.npz')
     n_views, n_objects, n_labels, n_ransac, ba_n_iter, seed = [int(x) for x in g['meta']]
@@ -147,17 +179,29 @@ def test_predict_scene_state_vs_reference(golden_dir, name):
     assert np.array_equal(out['ba_output'].infos['obj_id'].values, g['ba_output_obj_id'])
     assert len(out['ba_output+all_cand']) == int(g['n_all'][0])
     assert np.abs(out['ba_input'].poses.cpu().numpy() - g['ba_input_poses']).max() < 1e-5
-    # The world frame is a gauge freedom of the problem: the damped pseudo-inverse step moves it along
-    # a (numerically) null direction, so TWO / TWC themselves are not reproducible even by the reference
-    # across thread counts (measured: 9e-3 between 1 and 8 CPU threads) while every gauge-invariant
-    # quantity is (3e-5).  Compare those: object-in-camera poses and camera-to-camera transforms.
-    assert np.abs(out['ba_output'].poses.cpu().numpy() - g['ba_output_poses']).max() < 1e-3
+    # The world frame is a gauge freedom of the problem: the damped step moves it along a (numerically) null
+    # direction, so TWO / TWC themselves are not reproducible even by the reference across thread counts (measured:
+    # 9e-3 between 1 and 8 CPU threads).  Every gauge-invariant quantity is compared: object-in-camera poses
+    # (ba_output), camera-to-camera transforms, objects in the first camera's frame.
+    # The LM normal equations are ill conditioned in fp32: the reference run in float64 (scene_state_*_fp64.npz,
+    # the same reference code on float64 tensors) is `ref32_minus_fp64` (1.1e-4 / 1.1e-5) away from the fp32
+    # reference, so the engine (float64 linearisation + solve on the device) is held to 1e-4 against the float64
+    # reference and to 1e-4 + that distance against the fp32 golden.
+    g64 = np.load(golden_dir / f'{name}_fp64.npz')
+    ours = out['ba_output'].poses.cpu().numpy().astype(np.float64)
+    assert np.array_equal(out['ba_output'].infos['view_id'].values, g64['ba_output_view_id'])
+    d64 = np.abs(ours - g64['ba_output_poses']).max()
+    d32 = np.abs(ours - g['ba_output_poses']).max()
+    print(name, 'ba_output vs reference fp64', d64, 'vs reference fp32', d32, 'ref32 vs ref64', float(g64['ref32_minus_fp64'][0]))
+    assert d64 < 1e-4
+    assert d32 < 1e-4 + float(g64['ref32_minus_fp64'][0])
+    tol = 1e-4 + float(g64['ref32_minus_fp64'][0]) * 3
     TWC, TWC_g = out['scene/cameras'].TWC.cpu().numpy(), g['cameras_TWC']
     rel = np.linalg.inv(TWC[:1]) @ TWC
     rel_g = np.linalg.inv(TWC_g[:1]) @ TWC_g
-    assert np.abs(rel - rel_g).max() < 1e-3
+    assert np.abs(rel - rel_g).max() < tol
     TWO, TWO_g = out['scene/objects'].TWO.cpu().numpy(), g['objects_TWO']
-    assert np.abs(np.linalg.inv(TWC[:1]) @ TWO - np.linalg.inv(TWC_g[:1]) @ TWO_g).max() < 1e-3
+    assert np.abs(np.linalg.inv(TWC[:1]) @ TWO - np.linalg.inv(TWC_g[:1]) @ TWO_g).max() < tol
     # BA must not move the scene away from the ground truth it was generated from
     err_in = np.abs(g['ba_input_poses'][:, :3, 3] - out['ba_output'].poses.cpu().numpy()[:, :3, 3]).max()
     assert err_in < 0.1

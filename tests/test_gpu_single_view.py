@@ -181,15 +181,19 @@ def test_get_predictions_zup_and_external_init(dev, golden_dir):
     det = tc.PandasTensorCollection(infos=w.infos(), bboxes=_d(w.boxes, dev))
     final, preds = pred.get_predictions(_d(w.images, dev), _d(w.K, dev), detections=det)
     g = np.load(golden_dir / 'single_view_zup.npz')
-    # The z-up initialisation (cosypose_ops.py:138-173) and the coarse iteration meet the 1e-4 bound with
-    # a wide margin (measured 3e-6).  The refiner iteration of THIS synthetic case crops the whole noisy
-    # frame at zoom ~1, where the random network amplifies any rounding difference ~100x: the reference
-    # itself moves by 4.4e-5 between 4 and 8 CPU threads (tests/test_oracle_golden.py), the CUDA-core
-    # fp32 path lands at 3.0e-5 and the tensor-core 3xTF32 path at 3.1e-4.  The final pose of this case
-    # is therefore held to 5e-4; every other end-to-end case is held to 1e-4.
+    # The refiner iteration of THIS synthetic case crops the whole noisy frame at zoom ~1, where the random network
+    # amplifies rounding ~20x per iteration: the reference run in float64 (single_view_zup_fp64.npz, the same
+    # reference code with model.double()) differs from the reference run in float32 by 9.5e-5 on the final pose
+    # (5e-6 after the coarse iteration), so the fp32 golden is itself only known to ~1e-4 here.  The engine is held to
+    # 1e-4 against the float64 reference - the exact result of the reference's arithmetic - and, like the fp32
+    # reference, to 2e-4 against the fp32 golden (two fp32 evaluations each within 1e-4 of the exact value).
+    g64 = np.load(golden_dir / 'single_view_zup_fp64.npz')
     assert np.abs(preds['coarse/iteration=1'].poses_input.cpu().numpy() - g['coarse/iteration=1/poses_input']).max() < 1e-5
     assert np.abs(preds['coarse/iteration=1'].poses.cpu().numpy() - g['coarse/iteration=1/poses']).max() < TOL_POSE
-    assert np.abs(final.poses.cpu().numpy() - g['final_poses']).max() < 5e-4
+    f = final.poses.cpu().numpy().astype(np.float64)
+    assert float(g64['ref32_minus_fp64'][0]) > 5e-5          # the premise above
+    assert np.abs(f - g64['final_poses']).max() < TOL_POSE
+    assert np.abs(f - g['final_poses']).max() < 2 * TOL_POSE
     # external init: n_coarse_iterations must be 0, key 'external_coarse' is reported
     init = preds['coarse/iteration=1']
     views.reset()
@@ -200,6 +204,40 @@ def test_get_predictions_zup_and_external_init(dev, golden_dir):
     assert (final2.poses - final.poses).abs().max() < 1e-6
     with pytest.raises(AssertionError):
         pred.get_predictions(_d(w.images, dev), _d(w.K, dev), data_TCO_init=init, n_coarse_iterations=1)
+
+
+def test_get_predictions_cfg2_all_hypotheses(dev, golden_dir):
+    """BASELINE.json configs[1] at full size against the reference itself (tests/golden/make_golden_r2.py):
+    every one of the 64 hypotheses, every iteration, within the north star's 1e-4."""
+    from cosypose_b200.utils import tensor_collection as tc
+    w = Workload(8, 8, 21, 1, 4)
+    pred, eng, views = build_predictor(w, 0, bsz_objects=64)
+    det = tc.PandasTensorCollection(infos=w.infos(), bboxes=_d(w.boxes, dev))
+    final, preds = pred.get_predictions(_d(w.images, dev), _d(w.K, dev), detections=det, n_coarse_iterations=1,
+                                        n_refiner_iterations=4)
+    g = np.load(golden_dir / 'single_view_cfg2.npz')
+    assert final.poses.shape == (64, 4, 4)
+    worst = 0.0
+    for k, v in preds.items():
+        err = np.abs(v.poses.cpu().numpy() - g[f'{k}/poses']).max()
+        worst = max(worst, err)
+        assert err < TOL_POSE, (k, err)
+    assert np.abs(final.poses.cpu().numpy() - g['final_poses']).max() < TOL_POSE
+    print('cfg2: worst |dTCO| over 5 iterations x 64 hypotheses', worst)
+    eng.close()
+
+
+def test_get_predictions_symmetric_labels(dev, golden_dir):
+    """Labels with 1 / 2 / 4 / 64 discrete symmetries through the single-view path (reference golden)."""
+    from cosypose_b200.utils import tensor_collection as tc
+    w = Workload(2, 4, 8, 1, 2, sym_counts=(1, 2, 4, 64))
+    pred, eng, views = build_predictor(w, 0, bsz_objects=8)
+    det = tc.PandasTensorCollection(infos=w.infos(), bboxes=_d(w.boxes, dev))
+    final, _ = pred.get_predictions(_d(w.images, dev), _d(w.K, dev), detections=det, n_coarse_iterations=1,
+                                    n_refiner_iterations=2)
+    g = np.load(golden_dir / 'single_view_sym64.npz')
+    assert np.abs(final.poses.cpu().numpy() - g['final_poses']).max() < TOL_POSE
+    eng.close()
 
 
 def test_uint8_views_match_float(small, dev):

@@ -54,3 +54,26 @@ def test_ba_oracle_jacobian_is_consistent():
         em, *_ = mo.ba_linearize(*args, TWO_9d - dp[:TWO_9d.numel()].view(-1, 9), TCW_9d - dp[TWO_9d.numel():].view(-1, 9), *kw)
         fd = -(ep - em) / (2 * eps)          # errors = y - yhat, J = d yhat
         assert (fd - J[:, col]).abs().max() < 1e-4 * max(1.0, J[:, col].abs().max().item())
+
+
+def test_ba_oracle_matches_reference_forward_jacobian(golden_dir):
+    """oracle/multiview_oracle.ba_linearize against errors / loss / Jacobian of the reference's own
+    MultiviewRefinement.forward_jacobian (tests/golden/ba_jacobian_ref.npz, make_golden_r2.golden_ba_jacobian):
+    the BA oracle is pinned to the reference, not only to finite differences of itself."""
+    import numpy as np
+    import torch
+    from helpers import Scene
+    from oracle import multiview_oracle as mo
+    g = np.load(golden_dir / 'ba_jacobian_ref.npz')
+    n_views, n_objects, n_labels, n_ransac, seed = [int(x) for x in g['meta']]
+    sc = Scene(n_views, n_objects, n_labels, g['sym_counts'], True, seed)
+    ci = g['cand_index']
+    cand_label = g['obj_label_id'][g['cand_obj']]
+    assert np.array_equal(cand_label, np.asarray(sc.label_ids)[ci])
+    e, loss, J, _ = mo.ba_linearize(sc.poses[ci], g['cand_obj'], g['cand_view'], cand_label,
+                                    torch.from_numpy(g['TWO_9d']), torch.from_numpy(g['TCW_9d']), sc.K, sc.aabb,
+                                    sc.sym, sc.n_sym)
+    assert e.shape == g['errors'].shape and J.shape == g['J'].shape
+    assert np.abs(e.detach().numpy() - g['errors']).max() < 1e-4 * max(1.0, np.abs(g['errors']).max())
+    assert abs(loss.item() - float(g['loss'][0])) < 1e-5 * float(g['loss'][0])
+    assert np.abs(J.numpy() - g['J']).max() < 1e-5 * np.abs(g['J']).max()
