@@ -48,7 +48,11 @@ using namespace tc;   // PTX wrappers (mbarrier, bulk copy, tcgen05 alloc/commit
 constexpr int BM = 128;
 constexpr int BK = 32;                 // fp32 elements of A per k-stage
 constexpr int KSTEPS = BK / 16;        // kind::f16 MMAs are K = 16
-constexpr int DS = 2;                  // k-stages accumulated in TMEM between drains
+#ifndef PW2_DS
+#define PW2_DS 1
+#endif
+constexpr int DS = PW2_DS;             // k-stages accumulated in TMEM between drains
+constexpr float RZ_COMP = 7.7e-8f;     // expected relative loss of one drain group to the accumulator's round-toward-zero
 constexpr int BN_MAX = 192;
 constexpr int BN_SMALL = 96;
 constexpr int CONV_THREADS = 128;      // one converter group
@@ -319,11 +323,18 @@ k_pw2(const float* __restrict__ A, const __half* __restrict__ Wpk, const float* 
           const uint32_t b_hi = b_base + bslot * bsb, b_lo = b_hi + bsb / 2;
           const uint32_t d = tmem_base + b * ACC_STRIDE;
           const uint64_t dbh0 = make_desc(b_hi, lbo, 128), dbl0 = make_desc(b_lo, lbo, 128);
+          // The accumulator add rounds toward zero: every MMA costs up to one ulp of the CURRENT accumulator value,
+          // always in the same direction.  The small cross terms go in while the accumulator is still small (they
+          // then cost nothing), the two full-magnitude hi*hi MMAs last.
 #pragma unroll
           for (int j = 0; j < KSTEPS; ++j) {
             const uint64_t koff = (uint64_t)((j * 2 * lbo) >> 4);   // two 8-k chunks of B per MMA; 8 TMEM columns of A
-            umma_f16_ts_pred(d, a_lo + j * 8, dbh0 + koff, idesc, (first && j == 0) ? 0u : 1u);   // small terms first
+            umma_f16_ts_pred(d, a_lo + j * 8, dbh0 + koff, idesc, (first && j == 0) ? 0u : 1u);
             umma_f16_ts_pred(d, a_hi + j * 8, dbl0 + koff, idesc, 1);
+          }
+#pragma unroll
+          for (int j = 0; j < KSTEPS; ++j) {
+            const uint64_t koff = (uint64_t)((j * 2 * lbo) >> 4);
             umma_f16_ts_pred(d, a_hi + j * 8, dbh0 + koff, idesc, 1);
           }
           if (!resident) umma_commit_elect(emptyB(bslot));
@@ -451,7 +462,13 @@ k_pw2(const float* __restrict__ A, const __half* __restrict__ Wpk, const float* 
             }
             float o[32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = fmaf(acc[cc + i], inv_wscale, s_bias[c_base + cc + i]);
+            for (int i = 0; i < 32; ++i) {
+              // acc (1 + RZ_COMP) with ONE round-to-nearest: undoes the EXPECTED loss of the round-toward-zero
+              // accumulator adds (every drain group loses the same relative amount, so the sum does too; measured on
+              // same-sign operands: -7.7e-8 with this MMA order).  1 + 7.7e-8 is not a float, hence the FMA form.
+              const float a = fmaf(acc[cc + i], RZ_COMP, acc[cc + i]);
+              o[i] = fmaf(a, inv_wscale, s_bias[c_base + cc + i]);
+            }
             if (SWISH) {
 #pragma unroll
               for (int i = 0; i < 32; ++i) o[i] = swishf(o[i]);
