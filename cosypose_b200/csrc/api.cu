@@ -339,7 +339,7 @@ static int launch_xdw_inst(const xdw::Plan& p, cosyb200_handle* h, const BlockSp
   xdw::k_xdw<KS, S, NX, CCT, RH><<<std::min(n_items, h->n_sms), xdw::THREADS, p.smem_bytes, st>>>(
       x, (const __half*)w.expand_x, w.expand_x_inv, w.dw_w, w.dw_bias, out, h->pool_partial, B, b.hin, b.win, b.cin,
       b.cexp, b.hout, b.wout, b.pad_lo, p.MT, p.TH, p.TW, p.IH, p.IW, p.tiles_y, p.tiles_x, p.n_chunks, p.Kp,
-      p.NYS, h->cur_block == h->trace_block ? 1 : 0);
+      p.NYS, p.e_rows, h->cur_block == h->trace_block ? 1 : 0);
   CB_LAUNCH_CHECK();
   return 0;
 }
@@ -522,11 +522,11 @@ int cosyb200_create(cosyb200_handle** out, int device, int max_batch) {
     rc |= opt_in_gemm_kernels<true, false, false>();
     rc |= opt_in_gemm_kernels<true, false, true>();
     rc |= opt_in_gemm_kernels<false, false, false>();
-    rc |= opt_in_smem(xdw::k_xdw<3, 2, 1, 48, 3>, 200 * 1024);
-    rc |= opt_in_smem(xdw::k_xdw<3, 1, 2, 64, 6>, 200 * 1024);
-    rc |= opt_in_smem(xdw::k_xdw<5, 2, 1, 64, 3>, 200 * 1024);
-    rc |= opt_in_smem(xdw::k_xdw<5, 1, 2, 48, 5>, 200 * 1024);
-    rc |= opt_in_smem(xdw::k_xdw<3, 2, 2, 48, 2>, 200 * 1024);
+    rc |= opt_in_smem(xdw::k_xdw<3, 2, 1, 48, 3>, 208 * 1024);
+    rc |= opt_in_smem(xdw::k_xdw<3, 1, 2, 64, 6>, 208 * 1024);
+    rc |= opt_in_smem(xdw::k_xdw<5, 2, 1, 64, 3>, 208 * 1024);
+    rc |= opt_in_smem(xdw::k_xdw<5, 1, 2, 48, 5>, 208 * 1024);
+    rc |= opt_in_smem(xdw::k_xdw<3, 2, 2, 48, 2>, 208 * 1024);
     rc |= opt_in_smem(k_roi_crop, (int)(CROP_SMEM_FLOATS * sizeof(float)));
     rc |= opt_in_smem(k_se_gate, 100 * 1024);
     rc |= opt_in_smem(k_dw_tile<5, 1, 40, 1>, 80 * 1024);

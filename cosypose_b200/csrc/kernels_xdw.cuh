@@ -13,9 +13,12 @@
 //
 // One CTA per SM, persistent over items = (hypothesis, spatial tile); an item walks over all chunks of `cc`
 // (48 or 64) expanded channels:
-//   workers (16 warps)  per item: x rows of the halo tile -> fp16 hi/lo split -> TMEM (A operand, resident for all
-//                       chunks; thread = tile row = TMEM lane; double buffered, the next item's rows are loaded
-//                       and converted under the last chunk of the current item);
+//   workers (16 warps)  two groups of 8 warps that take ALTERNATE chunks (group g owns accumulator buffer g and its own
+//                       E tile), so the MUFU-bound drain of one chunk runs against the FMA / shared-memory bound
+//                       depthwise phase of the other instead of all 16 warps sitting on the same pipe;
+//                       per item: x rows of the halo tile -> fp16 hi/lo split -> TMEM (A operand, resident for all
+//                       chunks; thread = tile row = TMEM lane; double buffered, each group converts half of the k
+//                       units of the next item's rows under its last chunk of the current item);
 //                       per chunk: drain the accumulator (tcgen05.ld), swish -> shared-memory tile E[pixel][channel];
 //                       then the depthwise convolution from shared memory with a rolling register window (lane =
 //                       channel PAIR: 64-bit conflict-free loads, packed FFMA2), bias + swish, 256-byte row stores
@@ -45,6 +48,7 @@ using pw2::umma_f16_ts_pred;
 
 constexpr int NWW = 16;                 // worker warps
 constexpr int WORKERS = NWW * 32;
+constexpr int GROUP_WARPS = NWW / 2, GROUP_THREADS = GROUP_WARPS * 32;   // two worker groups on alternate chunks
 constexpr int MMA_WARP = NWW, LOADER_WARP = NWW + 1;
 constexpr int THREADS = (NWW + 4) * 32;      // warps 18-19 only complete the fifth warpgroup (setmaxnreg is per warpgroup)
 constexpr int CC_MAX = 64;              // expanded channels per chunk (= MMA N): 48 or 64
@@ -54,7 +58,7 @@ constexpr int MAX_XU = 2;               // 16-k units of the A row a worker thre
 constexpr uint32_t TMEM_COLS = 512;
 
 struct Plan {
-  int ok, MT, TH, TW, IH, IW, tiles_y, tiles_x, cc, n_chunks, Kp, NX, NYS, RH, smem_bytes;
+  int ok, MT, TH, TW, IH, IW, tiles_y, tiles_x, cc, n_chunks, Kp, NX, NYS, RH, e_rows, smem_bytes;
 };
 
 typedef unsigned long long u64;
@@ -124,17 +128,18 @@ __global__ void __launch_bounds__(THREADS, 1)
 k_xdw(const float* __restrict__ x, const __half* __restrict__ Wx, float inv_wscale, const float* __restrict__ dw_w,
       const float* __restrict__ dw_bias, float* __restrict__ out, float* __restrict__ partial, int B, int H, int W,
       int Cin, int Cexp, int Ho, int Wo, int pad, int MT, int TH, int TW, int IH, int IW, int tiles_y, int tiles_x,
-      int n_chunks, int Kp, int NYS, int do_trace) {
+      int n_chunks, int Kp, int NYS, int e_rows, int do_trace) {
   constexpr int cc = CCT;                                           // expanded channels per chunk (MMA N)
   constexpr int NIN = (NX - 1) * S + KS;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[10];
   __shared__ uint32_t s_tmem;
-  __shared__ __align__(8) float s_ps[MAX_UNITS * 64];
+  __shared__ __align__(8) float s_ps[2][MAX_UNITS * 64];
   const uint32_t b_base = (smem_u32(smem_raw) + 127u) & ~127u;
   const uint32_t b_bytes = (uint32_t)Kp * cc * 4u;                  // hi + lo image of one chunk
-  const uint32_t e_base = b_base + 2 * b_bytes;
+  const uint32_t e_base0 = b_base + 2 * b_bytes;
   constexpr int EP = cc + 4;                                        // floats per E row (16-byte row stores conflict free)
+  const uint32_t e_bytes = (uint32_t)e_rows * EP * 4u;              // one E tile (one per worker group)
   const int tid = threadIdx.x, lane = tid % 32;
   const int warp = __shfl_sync(0xffffffffu, tid / 32, 0);
   const int tiles = tiles_y * tiles_x;
@@ -155,7 +160,7 @@ k_xdw(const float* __restrict__ x, const __half* __restrict__ Wx, float inv_wsca
       mbar_init(fullB(s), 1);
       mbar_init(emptyB(s), 1);
       mbar_init(acc_full(s), 1);
-      mbar_init(acc_empty(s), WORKERS);
+      mbar_init(acc_empty(s), GROUP_THREADS);
     }
     fence_barrier_init();
   }
@@ -168,14 +173,17 @@ k_xdw(const float* __restrict__ x, const __half* __restrict__ Wx, float inv_wsca
   if (warp < NWW) {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");   // 16 x 32 x (112 - 96) = what the fifth warpgroup releases (96 -> 32)
     // ------------------------------------------------------------------ workers
-    const int q = warp % 4, part = warp / 4;
-    const int nsub = 4 / MT;                                   // sub-parts (k units / column ranges) per m-tile
-    const int mt = part % MT, sub = part / MT;
-    const bool part_on = part < MT * nsub;
+    const int group = warp / GROUP_WARPS, gw = warp % GROUP_WARPS;
+    const int q = warp % 4;
+    const int mt = gw / 4;                                     // MT == 2: the 8 warps of a group cover both m-tiles
+    const int sub = group, nsub = 2;                           // k units of the A rows this group converts
+    const bool part_on = mt < MT;
     const int row = mt * 128 + q * 32 + lane;                  // tile row (halo pixel) == TMEM lane of m-tile mt
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
     const int py = row / IW, px = row % IW;
-    const int CW = cc / nsub;                                  // accumulator columns this thread drains per chunk
+    const uint32_t e_base = e_base0 + (uint32_t)group * e_bytes;
+    float* s_psg = s_ps[group];
+    const int gtid = tid - group * GROUP_THREADS;
     const int n_xu = Kp / 16;
     float xv[MAX_XU][16];
     bool x_valid = false;
@@ -229,21 +237,25 @@ k_xdw(const float* __restrict__ x, const __half* __restrict__ Wx, float inv_wsca
 
     const int NXS = (TW + NX - 1) / NX;
     const int n_units = NXS * NYS;
-    int gch = 0;                                               // chunks processed by this CTA so far
-    int local_it = 0;
-    if ((int)blockIdx.x < n_items) {
+    (void)gw;
+    const int my_items = (int)blockIdx.x < n_items ? (n_items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const int total_chunks = my_items * n_chunks;
+    if (my_items > 0) {
       load_x(blockIdx.x);
       convert_x(0);
     }
-    for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++local_it) {
-      const int img = it / tiles, tile = it % tiles;
-      const int oy0 = (tile / tiles_x) * TH, ox0 = (tile % tiles_x) * TW;
-      const int next = it + gridDim.x;
-      for (int ch = 0; ch < n_chunks; ++ch, ++gch) {
-        const int buf = gch & 1;
-        const bool prep_next = ch == n_chunks - 1 && next < n_items;
-        const bool tr = do_trace && tid == 0 && gch < 16;
-        if (tr) trace(512 + 8 * gch);
+    for (int gch = group; gch < total_chunks; gch += 2) {      // this group's chunks; accumulator buffer == group
+      {
+        const int local_it = gch / n_chunks, ch = gch - local_it * n_chunks;
+        const int it = blockIdx.x + local_it * gridDim.x;
+        const int img = it / tiles, tile = it % tiles;
+        const int oy0 = (tile / tiles_x) * TH, ox0 = (tile % tiles_x) * TW;
+        const int next = it + gridDim.x;
+        const int buf = group;
+        // last chunk of this group inside the item: convert this group's half of the next item's rows
+        const bool prep_next = gch + 2 >= (local_it + 1) * n_chunks && next < n_items;
+        const bool tr = do_trace && tid == 0 && gch < 32;
+        if (tr) trace(512 + 8 * (gch >> 1));
         if (prep_next) load_x(next);                            // in flight under the accumulator wait and the drain
         // depthwise taps and bias of this lane's channel pair (the same for every unit of the chunk)
         const int c_local = 2 * lane;
@@ -260,13 +272,14 @@ k_xdw(const float* __restrict__ x, const __half* __restrict__ Wx, float inv_wsca
         if (!prep_next) load_w();                               // (with prep_next the registers hold the next item's rows)
         mbar_wait_warp(acc_full(buf), (gch >> 1) & 1);
         tc_fence_after();
-        if (tr) trace(512 + 8 * gch + 1);
+        if (tr) trace(512 + 8 * (gch >> 1) + 1);
         // ---- drain: swish of the accumulator (bias included, out-of-image rows are exact zeros)
         if (part_on) {
-          const uint32_t e_row = e_base + (uint32_t)(row * EP + sub * CW) * 4u;
-          const uint32_t t_acc = t_lane + buf * ACC_STRIDE + (uint32_t)(mt * cc + sub * CW);
+          const uint32_t e_row = e_base + (uint32_t)(row * EP) * 4u;
+          const uint32_t t_acc = t_lane + buf * ACC_STRIDE + (uint32_t)(mt * cc);
           const u64 inv2 = pk2(inv_wscale, inv_wscale);
-          for (int c0 = 0; c0 < CW; c0 += 8) {
+#pragma unroll 2
+          for (int c0 = 0; c0 < cc; c0 += 8) {
             u64 v[4];
             tmem_ld8_pairs(t_acc + c0, v);
 #pragma unroll
@@ -277,16 +290,16 @@ k_xdw(const float* __restrict__ x, const __half* __restrict__ Wx, float inv_wsca
         }
         tc_fence_before();
         mbar_arrive(acc_empty(buf));
-        if (tr) trace(512 + 8 * gch + 2);
+        if (tr) trace(512 + 8 * (gch >> 1) + 2);
         if (prep_next) {                                        // the MMAs of the next item start under this chunk's dw
           convert_x((local_it + 1) & 1);
           load_w();
         }
-        if (tr) trace(512 + 8 * gch + 3);
-        named_bar_sync(1, WORKERS);                             // #1: E complete
-        if (tr) trace(512 + 8 * gch + 4);
+        if (tr) trace(512 + 8 * (gch >> 1) + 3);
+        named_bar_sync(1 + group, GROUP_THREADS);               // #1: this group's E complete
+        if (tr) trace(512 + 8 * (gch >> 1) + 4);
         // ---- depthwise from E: unit = (x segment, y segment); lane = channel pair
-        for (int u = warp; u < n_units; u += NWW) {
+        for (int u = gw; u < n_units; u += GROUP_WARPS) {
           const int xs = u % NXS, ys = u / NXS;
           const int oyr0 = ys * RH, oxr0 = xs * NX;
           const int rows_here = min(RH, min(TH, Ho - oy0) - oyr0);
@@ -341,15 +354,15 @@ k_xdw(const float* __restrict__ x, const __half* __restrict__ Wx, float inv_wsca
           }
           float pa, pb;
           upk2(psum, pa, pb);
-          *reinterpret_cast<float2*>(&s_ps[u * 64 + c_local]) = make_float2(pa, pb);
+          *reinterpret_cast<float2*>(&s_psg[u * 64 + c_local]) = make_float2(pa, pb);
         }
-        if (tr) trace(512 + 8 * gch + 5);
-        named_bar_sync(1, WORKERS);                             // #2: E consumed, s_ps complete
-        if (tr) trace(512 + 8 * gch + 6);
-        if (tid < cc) {
+        if (tr) trace(512 + 8 * (gch >> 1) + 5);
+        named_bar_sync(1 + group, GROUP_THREADS);               // #2: E consumed, s_ps complete
+        if (tr) trace(512 + 8 * (gch >> 1) + 6);
+        if (gtid < cc) {
           float s = 0.f;
-          for (int v = 0; v < n_units; ++v) s += s_ps[v * 64 + tid];
-          partial[((size_t)img * tiles + tile) * Cexp + ch * cc + tid] = s;
+          for (int v = 0; v < n_units; ++v) s += s_psg[v * 64 + gtid];
+          partial[((size_t)img * tiles + tile) * Cexp + ch * cc + gtid] = s;
         }
       }
     }
@@ -443,7 +456,9 @@ inline Plan make_plan(const BlockSpec& b) {
   p.RH = (p.TH + p.NYS - 1) / p.NYS;
   // the last y segment computes (never stores) rows past the tile when TH is not a multiple of RH
   const int e_rows = std::max(p.MT * 128, ((p.NYS * p.RH - 1) * b.s + b.k) * p.IW);
-  p.smem_bytes = 128 + 2 * p.Kp * p.cc * 4 + (e_rows + E_SLACK_ROWS) * (p.cc + 4) * 4;
+  p.e_rows = e_rows + E_SLACK_ROWS;
+  p.smem_bytes = 128 + 2 * p.Kp * p.cc * 4 + 2 * p.e_rows * (p.cc + 4) * 4;
+  if (p.n_chunks < 2 || p.smem_bytes > 208 * 1024) return p;   // + 16.5 KB static = the 227 KB an SM offers
   p.ok = 1;
   return p;
 }
