@@ -557,7 +557,13 @@ def _reference_multiview_step():
 
 def cpu_baseline(cfg, sample_hyps, steps=1, warmup=1):
     """Bounded CPU sample of the same workload: all host cores, plus a smaller 1-thread sample (the reference's own
-    default, cosypose/__init__.py:2-3)."""
+    default, cosypose/__init__.py:2-3).  The reference prints on import: stdout carries the JSON line only."""
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):
+        return _cpu_baseline(cfg, sample_hyps, steps, warmup)
+
+
+def _cpu_baseline(cfg, sample_hyps, steps=1, warmup=1):
     cores = os.cpu_count()
     if cfg == 3:
         if not _reference_available():
@@ -589,9 +595,16 @@ def run_reference(args, cfg, rank):
     sample of the workload, sized from a probe so that the K + W steps end within a few minutes."""
     if rank != 0:
         return
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):
+        line = _run_reference(args, cfg)
+    print(json.dumps(line))
+
+
+def _run_reference(args, cfg):
     cores = os.cpu_count()
     if cfg == 3:
-        cb = cpu_baseline(3, 0, steps=max(1, args.steps), warmup=min(args.warmup, 1))
+        cb = _cpu_baseline(3, 0, steps=max(1, args.steps), warmup=min(args.warmup, 1))
         value, unit, ms = cb['value'], 'scenes/s', 1e3 / cb['value'] if cb['value'] else None
     else:
         use_ref = _reference_available()
@@ -620,7 +633,7 @@ def run_reference(args, cfg, rank):
                 data='synthetic', impl='reference', config={'workload': f"{c['name']}: {c['text']}"},
                 cpu_baseline=cb,
                 e2e={'value': value, 'unit': unit, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0})
-    print(json.dumps(line))
+    return line
 
 
 def main():

@@ -88,6 +88,10 @@ def gather_records(local, n_total, engine=None):
     out[rank * per: rank * per + local.shape[0]] = local
     if engine is not None and getattr(engine, 'nccl_ready', False):
         engine.allgather_candidates(out)                     # in place: this rank's rows are already there
+    elif out.is_cuda and dist.get_backend() == 'gloo':          # test rigs without one GPU per rank
+        host = out.cpu()
+        dist.all_gather_into_tensor(host, host[rank * per:(rank + 1) * per].clone())
+        out.copy_(host)
     else:
         dist.all_gather_into_tensor(out, out[rank * per:(rank + 1) * per].clone())
     return out[:n_total]
