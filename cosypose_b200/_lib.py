@@ -62,6 +62,7 @@ _SIGS = {
     'cosyb200_lm_solve': ([_P, c_int, _P, _P, c_double, _P, _P, _P], c_int),
     'cosyb200_ransac_inliers': ([c_int64, _P, _P, c_int64, _P, _P, _P, _P, c_float, c_int, _P, _P,
                                  POINTER(c_int64), _P, POINTER(c_int64)], c_int),
+    'cosyb200_ransac_inliers_dev': ([_P, c_int64, c_int64, _P, c_int64, _P, _P, _P, _P, c_float, c_int, _P, _P, _P, _P, _P], c_int),
     'cosyb200_scatter_argmin': ([c_int64, _P, _P, c_int64, _P], c_int),
     'cosyb200_expand_ids_for_symmetry': ([c_int64, _P, _P, POINTER(c_int64), _P, _P], c_int),
 }

@@ -581,7 +581,7 @@ int cosyb200_destroy(cosyb200_handle* h) {
   free_model(h->models[1]);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   void* ptrs[] = {h->act[0], h->act[1], h->buf_e, h->buf_d, h->pool_partial, h->gate, h->crops, h->pose9,
-                  h->pts_sampled, h->sym, h->n_sym, h->aabb, h->io_buf, h->ba_ws, h->lm_ws};
+                  h->pts_sampled, h->sym, h->n_sym, h->aabb, h->io_buf, h->ba_ws, h->lm_ws, h->vote_ws};
   for (void* p : ptrs) if (p) cudaFree(p);
   delete h;
   return COSYB200_OK;
@@ -788,7 +788,7 @@ int cosyb200_tco_init(cosyb200_handle* h, int B, int zup, const float* boxes, co
   if (zup) { if (!h->pts_sampled) { set_error("tco_init: meshes not set"); return COSYB200_ESTATE; } }
   DeviceGuard guard(h->device);
   LaunchScope ls(h, CAT_GEOMETRY, (cudaStream_t)stream);
-  k_tco_init<<<B, GEO_THREADS, 0, (cudaStream_t)stream>>>(B, zup, boxes, K, label_ids, h->pts_sampled, N_SAMPLE, TCO);
+  k_tco_init<<<B, GEO_THREADS, 0, (cudaStream_t)stream>>>(B, zup, boxes, K, label_ids, h->n_labels, h->pts_sampled, N_SAMPLE, TCO);
   CB_LAUNCH_CHECK();
   return COSYB200_OK;
 }
@@ -802,7 +802,7 @@ int cosyb200_prepare_iter(cosyb200_handle* h, int B, int img_h, int img_w, const
   DeviceGuard guard(h->device);
   float aspect = (float)((double)std::max(img_h, img_w) / (double)std::min(img_h, img_w));
   LaunchScope ls(h, CAT_GEOMETRY, (cudaStream_t)stream);
-  k_project_boxes<<<B, GEO_THREADS, 0, (cudaStream_t)stream>>>(B, K, TCO, label_ids, h->pts_sampled, N_SAMPLE,
+  k_project_boxes<<<B, GEO_THREADS, 0, (cudaStream_t)stream>>>(B, K, TCO, label_ids, h->n_labels, h->pts_sampled, N_SAMPLE,
                                                               aspect, boxes_rend, boxes_crop, K_crop);
   CB_LAUNCH_CHECK();
   return COSYB200_OK;
@@ -1250,6 +1250,54 @@ int cosyb200_ba_linearize(cosyb200_handle* h, int n_cand, int n_obj, int n_view,
     k_ba_normal<<<grid, block, 0, st>>>(n_cand, n_pts, n_obj, n_view, cand_obj, cand_view, Jc, errors, JtJ, Jte);
     CB_LAUNCH_CHECK();
   }
+  return COSYB200_OK;
+}
+
+// find_ransac_inliers on the device (kernels_ransac.cuh, namespace vote): everything stays on the GPU until the two
+// counters and the (short) ordered lists are read back by the caller.
+int cosyb200_ransac_inliers_dev(cosyb200_handle* h, int64_t n_seeds, int64_t n_pairs, const int32_t* pair_start_dev,
+                                int64_t n_mtc, const int32_t* mtc_hyp_dev, const int32_t* mtc_c1_dev,
+                                const int32_t* mtc_c2_dev, const float* dists_dev, float thr, int n_min_inliers,
+                                int32_t* out_c1_dev, int32_t* out_c2_dev, int32_t* best_dev, int64_t* counts_dev,
+                                void* stream) {
+  CB_CHECK_ARG(h != nullptr && n_seeds >= 1 && n_pairs >= 1 && n_mtc >= 1 && n_mtc < (1ll << 31), "ransac_inliers_dev: bad sizes");
+  CB_CHECK_ARG(pair_start_dev && mtc_hyp_dev && mtc_c1_dev && mtc_c2_dev && dists_dev && out_c1_dev && out_c2_dev &&
+               best_dev && counts_dev, "ransac_inliers_dev: null pointer");
+  DeviceGuard guard(h->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  // workspace: flags u8 [n_mtc] | acc_rows i32 [n_mtc] | row_start, n_inl i32 [n_seeds] | dsum f32 [n_seeds] |
+  //            best_h, cnt i32 [n_pairs]
+  const size_t need = (size_t)n_mtc * 8 + (size_t)n_seeds * 12 + (size_t)n_pairs * 8 + 64;
+  if (h->vote_ws_bytes < need) {
+    if (h->vote_ws) { CB_CUDA(cudaStreamSynchronize(st)); cudaFree(h->vote_ws); h->vote_ws = nullptr; }
+    CB_CUDA(cudaMalloc(&h->vote_ws, need));
+    h->vote_ws_bytes = need;
+  }
+  int32_t* acc_rows = (int32_t*)h->vote_ws;
+  int32_t* row_start = acc_rows + n_mtc;
+  int32_t* n_inl = row_start + n_seeds;
+  float* dsum = (float*)(n_inl + n_seeds);
+  int32_t* best_h = (int32_t*)(dsum + n_seeds);
+  int32_t* cnt = best_h + n_pairs;
+  uint8_t* flags = (uint8_t*)(cnt + n_pairs);
+  {
+    LaunchScope ls(h, CAT_RANSAC, st);
+    vote::k_vote_greedy<<<(unsigned)((n_seeds + vote::WARPS - 1) / vote::WARPS), vote::WARPS * 32, 0, st>>>(
+        (int)n_seeds, (int)n_mtc, mtc_hyp_dev, mtc_c1_dev, mtc_c2_dev, dists_dev, thr, flags, acc_rows, row_start, n_inl, dsum);
+  }
+  CB_LAUNCH_CHECK();
+  {
+    LaunchScope ls(h, CAT_RANSAC, st);
+    vote::k_vote_best<<<(unsigned)((n_pairs + vote::WARPS - 1) / vote::WARPS), vote::WARPS * 32, 0, st>>>(
+        (int)n_pairs, pair_start_dev, n_inl, dsum, n_min_inliers, best_h, cnt);
+  }
+  CB_LAUNCH_CHECK();
+  {
+    LaunchScope ls(h, CAT_RANSAC, st);
+    vote::k_vote_emit<<<1, 1024, 0, st>>>((int)n_pairs, best_h, cnt, row_start, acc_rows, mtc_c1_dev, mtc_c2_dev,
+                                         out_c1_dev, out_c2_dev, best_dev, counts_dev);
+  }
+  CB_LAUNCH_CHECK();
   return COSYB200_OK;
 }
 

@@ -135,6 +135,7 @@ struct cosyb200_handle {
   uint64_t model_epoch = 0;            // bumped whenever weights or mesh tables are (re)loaded: invalidates the graphs
   cudaStream_t cap_stream = nullptr;   // capture happens here (the caller's stream may be the legacy stream)
   double* ba_ws = nullptr; size_t ba_ws_elems = 0;   // float64 residuals + compact Jacobian of ba_linearize_f64
+  void* vote_ws = nullptr; size_t vote_ws_bytes = 0;   // scratch of ransac_inliers_dev
   double* lm_ws = nullptr; size_t lm_ws_elems = 0;   // Cholesky workspace of lm_solve
   void* nccl_comm = nullptr;   // ncclComm_t created by cosyb200_nccl_comm_init
   int nccl_world = 1, nccl_rank = 0;

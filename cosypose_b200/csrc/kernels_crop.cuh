@@ -69,7 +69,7 @@ k_roi_crop(int B, const float* __restrict__ images, int n_images, int H, int W,
   const float roi_h = fmaxf(__fsub_rn(y2, y1), 1.0f);
   const float bin_w = __fdiv_rn(roi_w, (float)RENDER_W);
   const float bin_h = __fdiv_rn(roi_h, (float)RENDER_H);
-  const float* img = images + (size_t)im_ids[b] * 3 * H * W;
+  const float* img = images + (size_t)min(max(im_ids[b], 0), n_images - 1) * 3 * H * W;   // ids outside the batch are clamped
 
   AxisSample sx[4];
 #pragma unroll

@@ -28,7 +28,7 @@ constexpr int GEO_THREADS = 128;
 
 __global__ void __launch_bounds__(GEO_THREADS)
 k_project_boxes(int B, const float* __restrict__ K, const float* __restrict__ TCO,
-                const int32_t* __restrict__ label_ids, const float* __restrict__ pts_sampled,
+                const int32_t* __restrict__ label_ids, int n_labels, const float* __restrict__ pts_sampled,
                 int n_sample, float img_aspect, float* __restrict__ boxes_rend,
                 float* __restrict__ boxes_crop, float* __restrict__ K_crop) {
   const int b = blockIdx.x;
@@ -49,7 +49,7 @@ k_project_boxes(int B, const float* __restrict__ K, const float* __restrict__ TC
   float P[12];
 #pragma unroll
   for (int i = 0; i < 12; ++i) P[i] = sP[i];
-  const float* pts = pts_sampled + (size_t)label_ids[b] * n_sample * 3;
+  const float* pts = pts_sampled + (size_t)min(max(label_ids[b], 0), n_labels - 1) * n_sample * 3;   // ids outside the table are clamped
   float umin = INFINITY, vmin = INFINITY, umax = -INFINITY, vmax = -INFINITY;
   for (int i = threadIdx.x; i < n_sample; i += GEO_THREADS) {
     float x = pts[i * 3 + 0], y = pts[i * 3 + 1], z = pts[i * 3 + 2];
@@ -165,7 +165,7 @@ __global__ void k_update_pose(int B, const float* __restrict__ TCO, const float*
 // TCO_init_from_boxes_zup_autodepth             lib3d/cosypose_ops.py:138-173   (zup == 1)
 __global__ void __launch_bounds__(GEO_THREADS)
 k_tco_init(int B, int zup, const float* __restrict__ boxes, const float* __restrict__ K,
-           const int32_t* __restrict__ label_ids, const float* __restrict__ pts_sampled, int n_sample,
+           const int32_t* __restrict__ label_ids, int n_labels, const float* __restrict__ pts_sampled, int n_sample,
            float* __restrict__ TCO) {
   const int b = blockIdx.x;
   if (b >= B) return;
@@ -186,7 +186,7 @@ k_tco_init(int B, int zup, const float* __restrict__ boxes, const float* __restr
   // z-up + auto-depth: R = [[0,1,0],[0,0,-1],[-1,0,0]], z_guess = 1
   __shared__ float sred[4][GEO_THREADS / 32];
   const float tx = ((uc - cx) * 1.f) / fx, ty = ((vc - cy) * 1.f) / fy;
-  const float* pts = pts_sampled + (size_t)label_ids[b] * n_sample * 3;
+  const float* pts = pts_sampled + (size_t)min(max(label_ids[b], 0), n_labels - 1) * n_sample * 3;   // ids outside the table are clamped
   float xmin = INFINITY, xmax = -INFINITY, ymin = INFINITY, ymax = -INFINITY;
   for (int i = threadIdx.x; i < n_sample; i += GEO_THREADS) {
     float py = pts[i * 3 + 1], pz = pts[i * 3 + 2];

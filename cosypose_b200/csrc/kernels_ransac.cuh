@@ -196,4 +196,132 @@ k_ransac_score(int64_t n, const float* __restrict__ poses, const int32_t* __rest
   if (lane == 0 && live) dists[row] = d;
 }
 
+
+// ---- device-side inlier voting ------------------------------------------------------------------------------
+// cosypose_cext.find_ransac_inliers (reference: csrc/cosypose_cext.cpp:107-216) without the device -> host copy of
+// the distances: same integers out, bit for bit (tests/test_gpu_multiview.py compares with the host implementation,
+// which is itself pinned to the reference's compiled extension).
+//   k_vote_greedy   one warp per hypothesis: rows with dist <= thr, greedy one-to-one matching in ascending
+//                   (dist, row) order = the reference's stable sort + first-fit scan, as "repeatedly take the smallest
+//                   still-eligible row"; fp32 sum of the accepted distances in acceptance order.
+//   k_vote_best     one warp per ordered view pair: most inliers (>= n_min), ties by smaller distance sum, then by
+//                   lower hypothesis id; a pair whose best hypothesis is id 0 is dropped (cosypose_cext.cpp:203).
+//   k_vote_emit     exclusive scan over the pairs (one block) and the ordered lists of inlier matches / best ids.
+namespace vote {
+constexpr int WARPS = 8;
+
+__device__ __forceinline__ int lower_bound_i32(const int32_t* __restrict__ a, int n, int key) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (a[mid] < key) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(WARPS * 32)
+k_vote_greedy(int n_seeds, int n_mtc, const int32_t* __restrict__ hyp, const int32_t* __restrict__ c1,
+              const int32_t* __restrict__ c2, const float* __restrict__ dists, float thr, uint8_t* __restrict__ flags,
+              int32_t* __restrict__ acc_rows, int32_t* __restrict__ row_start, int32_t* __restrict__ n_inl,
+              float* __restrict__ dsum) {
+  const int h = blockIdx.x * WARPS + threadIdx.x / 32, lane = threadIdx.x % 32;
+  if (h >= n_seeds) return;
+  const int lo = lower_bound_i32(hyp, n_mtc, h), hi = lower_bound_i32(hyp, n_mtc, h + 1);
+  for (int r = lo + lane; r < hi; r += 32) flags[r] = dists[r] <= thr ? 1 : 0;
+  __syncwarp();
+  int n = 0;
+  float sum = 0.f;
+  while (true) {
+    float bd = 0.f;
+    int br = 0x7fffffff;
+    for (int r = lo + lane; r < hi; r += 32) {
+      if (flags[r]) {
+        const float d = dists[r];
+        if (br == 0x7fffffff || d < bd) { bd = d; br = r; }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float od = __shfl_xor_sync(0xffffffffu, bd, o);
+      const int orr = __shfl_xor_sync(0xffffffffu, br, o);
+      if (orr != 0x7fffffff && (br == 0x7fffffff || od < bd || (od == bd && orr < br))) { bd = od; br = orr; }
+    }
+    if (br == 0x7fffffff) break;
+    const int a1 = c1[br], a2 = c2[br];
+    if (lane == 0) acc_rows[lo + n] = br;
+    sum += bd;
+    ++n;
+    for (int r = lo + lane; r < hi; r += 32)
+      if (c1[r] == a1 || c2[r] == a2) flags[r] = 0;
+    __syncwarp();
+  }
+  if (lane == 0) { n_inl[h] = n; dsum[h] = sum; row_start[h] = lo; }
+}
+
+__global__ void __launch_bounds__(WARPS * 32)
+k_vote_best(int n_pairs, const int32_t* __restrict__ pair_start, const int32_t* __restrict__ n_inl,
+            const float* __restrict__ dsum, int n_min, int32_t* __restrict__ best_h, int32_t* __restrict__ cnt) {
+  const int p = blockIdx.x * WARPS + threadIdx.x / 32, lane = threadIdx.x % 32;
+  if (p >= n_pairs) return;
+  int bh = -1, bn = 0;
+  float bs = 3.402823466e+38f;
+  for (int h = pair_start[p] + lane; h < pair_start[p + 1]; h += 32) {
+    const int n = n_inl[h];
+    const float s = dsum[h];
+    if (n >= n_min && (n > bn || (n == bn && s < bs))) { bh = h; bn = n; bs = s; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const int oh = __shfl_xor_sync(0xffffffffu, bh, o), on = __shfl_xor_sync(0xffffffffu, bn, o);
+    const float os = __shfl_xor_sync(0xffffffffu, bs, o);
+    // the sequential scan keeps the FIRST hypothesis among full ties: lower id wins
+    if (oh >= 0 && (bh < 0 || on > bn || (on == bn && (os < bs || (os == bs && oh < bh))))) { bh = oh; bn = on; bs = os; }
+  }
+  if (lane == 0) {
+    const bool keep = bh > 0;                     // id 0 can never be selected (cosypose_cext.cpp:203)
+    best_h[p] = keep ? bh : -1;
+    cnt[p] = keep ? bn : 0;
+  }
+}
+
+// single block: offsets of every kept pair, then the ordered outputs; counts[0] = inlier matches, counts[1] = pairs
+__global__ void __launch_bounds__(1024)
+k_vote_emit(int n_pairs, const int32_t* __restrict__ best_h, const int32_t* __restrict__ cnt,
+            const int32_t* __restrict__ row_start, const int32_t* __restrict__ acc_rows, const int32_t* __restrict__ c1,
+            const int32_t* __restrict__ c2, int32_t* __restrict__ out_c1, int32_t* __restrict__ out_c2,
+            int32_t* __restrict__ best_out, int64_t* __restrict__ counts) {
+  __shared__ int s_m[1024], s_b[1024];
+  const int tid = threadIdx.x;
+  const int per = (n_pairs + 1023) / 1024;
+  const int p0 = min(n_pairs, tid * per), p1 = min(n_pairs, p0 + per);
+  int m = 0, b = 0;
+  for (int p = p0; p < p1; ++p) { m += cnt[p]; b += best_h[p] > 0 ? 1 : 0; }
+  s_m[tid] = m;
+  s_b[tid] = b;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {            // inclusive Hillis-Steele scan of both counters
+    const int vm = tid >= o ? s_m[tid - o] : 0, vb = tid >= o ? s_b[tid - o] : 0;
+    __syncthreads();
+    s_m[tid] += vm;
+    s_b[tid] += vb;
+    __syncthreads();
+  }
+  int om = s_m[tid] - m, ob = s_b[tid] - b;
+  for (int p = p0; p < p1; ++p) {
+    const int h = best_h[p];
+    if (h > 0) {
+      best_out[ob++] = h;
+      const int lo = row_start[h];
+      for (int i = 0; i < cnt[p]; ++i) {
+        const int r = acc_rows[lo + i];
+        out_c1[om] = c1[r];
+        out_c2[om] = c2[r];
+        ++om;
+      }
+    }
+  }
+  if (tid == 1023) { counts[0] = s_m[1023]; counts[1] = s_b[1023]; }
+}
+}  // namespace vote
+
 }  // namespace cosyb

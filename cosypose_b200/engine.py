@@ -347,6 +347,34 @@ class Engine:
             _ptr(out['JtJ']), _ptr(out['Jte']), _ptr(out['loss']), self._stream()), 'ba_linearize')
         return out
 
+    def ransac_inliers_dev(self, seeds_view1, seeds_view2, d_tmatches, dists, dist_threshold, n_min_inliers):
+        """find_ransac_inliers on the device: seeds_view1/2 host int arrays (grouped by ordered view pair, as
+        ransac_infos emits them), d_tmatches [3, n_mtc] int32 and dists [n_mtc] float32 on the device.  Only the two
+        counters and the short ordered result lists are copied back."""
+        v1 = np.ascontiguousarray(seeds_view1, dtype=np.int64)
+        v2 = np.ascontiguousarray(seeds_view2, dtype=np.int64)
+        n_seeds, n_mtc = len(v1), d_tmatches.shape[1]
+        if n_seeds == 0 or n_mtc == 0:
+            e = np.zeros(0, dtype=np.int32)
+            return dict(inlier_matches_cand1=e, inlier_matches_cand2=e.copy(), best_hypotheses=e.copy())
+        key = v1 * (int(v2.max()) + 1 if n_seeds else 1) + v2
+        assert n_seeds >= 1 and np.all(np.diff(key) >= 0), 'seeds must be grouped by ascending (view1, view2)'
+        starts = np.flatnonzero(np.concatenate(([True], np.diff(key) != 0)))
+        pair_start = torch.from_numpy(np.concatenate((starts, [n_seeds])).astype(np.int32)).to(self.device)
+        n_pairs = len(starts)
+        self._chk(d_tmatches, torch.int32, (3, n_mtc), 'tmatches')
+        self._chk(dists, torch.float32, (n_mtc,), 'dists')
+        o1, o2 = self._new(n_mtc, dtype=torch.int32), self._new(n_mtc, dtype=torch.int32)
+        ob = self._new(n_pairs, dtype=torch.int32)
+        counts = self._new(2, dtype=torch.int64)
+        _lib.check(self._L.cosyb200_ransac_inliers_dev(
+            self._h, n_seeds, n_pairs, _ptr(pair_start), n_mtc, _ptr(d_tmatches[0]), _ptr(d_tmatches[1]),
+            _ptr(d_tmatches[2]), _ptr(dists), float(dist_threshold), int(n_min_inliers), _ptr(o1), _ptr(o2), _ptr(ob),
+            _ptr(counts), self._stream()), 'ransac_inliers_dev')
+        no, nb = (int(c) for c in counts.cpu())
+        return dict(inlier_matches_cand1=o1[:no].cpu().numpy(), inlier_matches_cand2=o2[:no].cpu().numpy(),
+                    best_hypotheses=ob[:nb].cpu().numpy())
+
     def ba_linearize_f64(self, cand_TCO, cand_obj, cand_view, cand_label, TWO_9d, TCW_9d, K, points,
                          residuals_threshold=25.0, normal_equations=True):
         """ba_linearize evaluated in float64 on the device: JtJ / Jte / loss are float64 device tensors."""

@@ -4,12 +4,12 @@
     seeds / tentative matches   engine.ransac_infos     host C++   (cosypose_cext.cpp:36-105)
     camera-pose hypotheses      Engine.ransac_models    one launch over ALL seeds (ransac.py:19-64)
     scoring                     Engine.ransac_score     one launch over ALL rows  (ransac.py:67-88)
-    inlier voting               engine.ransac_inliers   host C++   (cosypose_cext.cpp:107-216)
+    inlier voting               Engine.ransac_inliers_dev  three small launches (cosypose_cext.cpp:107-216)
     scene-level matching        scipy strongly-connected components, pandas (ransac.py:91-134)
 
 The reference chunks the two device stages (`model_bsz`, `score_bsz`) and synchronises per chunk for
-a host-side argmin (lib3d/symmetric_distances.py:13-16); here there is one device->host copy of the
-distances.  `model_bsz` / `score_bsz` are accepted and ignored.
+a host-side argmin (lib3d/symmetric_distances.py:13-16); here the distances stay on the device and only
+the voted integer lists come back.  `model_bsz` / `score_bsz` are accepted and ignored.
 """
 import numpy as np
 import pandas as pd
@@ -91,8 +91,9 @@ def multiview_candidate_matching(candidates, mesh_db, model_bsz=1e3, score_bsz=1
     timer_score.start()
     d_tm = torch.from_numpy(tmatches).to(eng.device)
     dists = eng.ransac_score(poses, d_labels, d_tm, TC1C2)
-    inliers = E.ransac_inliers(seeds[0], seeds[1], tmatches[0], tmatches[1], tmatches[2],
-                               dists.cpu().numpy(), dist_threshold, n_min_inliers)
+    # voting on the device (cosyb200_ransac_inliers_dev): the distances never leave the GPU; the host
+    # implementation E.ransac_inliers (bit-identical, pinned to the reference's extension) stays as the checker
+    inliers = eng.ransac_inliers_dev(seeds[0], seeds[1], d_tm, dists, dist_threshold, n_min_inliers)
     timer_score.pause()
 
     timer_misc.start()

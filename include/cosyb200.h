@@ -218,6 +218,19 @@ int cosyb200_ransac_inliers(int64_t n_seeds, const int32_t* seeds_view1_host,
                             int32_t* inlier_cand2_host, int64_t* n_inlier_matches,
                             int32_t* best_hypotheses_host, int64_t* n_best);
 
+/* The same voting on the device (no device -> host copy of the distances; reference: csrc/cosypose_cext.cpp:107-216,
+ * including the stable tie order and the id-0 quirk at :203).  Seeds must be grouped by ordered view pair in ascending
+ * (view1, view2) order, as cosyb200_ransac_infos emits them: pair_start_dev [n_pairs + 1] are the seed offsets of the
+ * pairs; the rows of one hypothesis must be contiguous and hypothesis ids ascending (also as emitted).
+ * out_c1 / out_c2 [capacity n_mtc], best [capacity n_pairs], counts [2] = {#inlier matches, #kept pairs} (int64). */
+int cosyb200_ransac_inliers_dev(cosyb200_handle* h, int64_t n_seeds, int64_t n_pairs,
+                                const int32_t* pair_start_dev, int64_t n_tmatches,
+                                const int32_t* tmatches_hyp_dev, const int32_t* tmatches_cand1_dev,
+                                const int32_t* tmatches_cand2_dev, const float* dists_dev,
+                                float dist_threshold, int n_min_inliers, int32_t* inlier_cand1_dev,
+                                int32_t* inlier_cand2_dev, int32_t* best_hypotheses_dev, int64_t* counts_dev,
+                                void* stream);
+
 /* cosypose_cext.scatter_argmin (reference: csrc/cosypose_cext.cpp:218-245): first minimum per
  * group; out_host has one entry per group id 0..n_groups-1. */
 int cosyb200_scatter_argmin(int64_t n, const float* values_host, const int32_t* group_ids_host,
@@ -270,6 +283,12 @@ int cosyb200_ba_linearize_f64(cosyb200_handle* h, int n_cand, int n_obj, int n_v
  * number of non-positive pivots that had to be replaced (0 for a positive definite system). */
 int cosyb200_lm_solve(cosyb200_handle* h, int n, const double* JtJ64_dev, const double* Jte64_dev, double lambda,
                       float* step_dev, int32_t* n_bad_pivots_dev, void* stream);
+
+/* Index preconditions.  label ids and image ids of the single-view entry points (tco_init, prepare_iter, roi_crop,
+ * refine_iter, refine_n) are clamped into their tables on the device, so a bad id cannot read out of bounds (its result
+ * is meaningless).  The multiview entry points (ransac_models / ransac_score / symmetric_distance / ransac_inliers_dev /
+ * ba_linearize*) take candidate, label, object and view ids that MUST be valid: they index caller-sized arrays whose
+ * lengths the ABI does not carry; the Python shim builds them from cosyb200_ransac_infos and dense label tables. */
 
 /* ---- multi-GPU exchange ----------------------------------------------------------
  * Hypotheses shard across ranks with no data-path collective; the ONE exchange is an all-gather of fixed-size fp32

@@ -127,6 +127,42 @@ def test_ba_linearize_vs_autograd_oracle():
         assert (rows[r] - dense).abs().max() < 1e-4 * dense.abs().max().clamp_min(1.0)
 
 
+@pytest.mark.parametrize('case', ['cfg4', 'ties', 'repeated_labels'])
+def test_device_voting_matches_host_bit_for_bit(case):
+    """cosyb200_ransac_inliers_dev against the host implementation (itself bit-exact vs the reference's compiled
+    extension, tests/test_abi.py): same inlier lists, same best hypotheses, same order - including exact distance
+    ties (stable order), distances on the threshold, NaNs, and a best hypothesis with id 0 (dropped by both)."""
+    from cosypose_b200 import engine as E
+    rs = np.random.RandomState(11)
+    if case == 'cfg4':
+        sc = Scene(8, 16, 21, (1,), True, 0)
+        view_ids, label_ids = np.asarray(sc.view_ids, dtype=np.int32), np.asarray(sc.label_ids, dtype=np.int32)
+        n_iter = 2000
+    elif case == 'ties':
+        view_ids = np.repeat(np.arange(4), 6).astype(np.int32)
+        label_ids = np.tile(np.arange(6), 4).astype(np.int32)
+        n_iter = 30
+    else:
+        view_ids = np.repeat(np.arange(3), 12).astype(np.int32)
+        label_ids = rs.randint(0, 3, size=36).astype(np.int32)       # many tentative matches per view pair
+        n_iter = 200
+    seeds, tmatches = E.ransac_infos(view_ids, label_ids, n_iter, 0)
+    n_mtc = tmatches.shape[1]
+    d = rs.uniform(0.0, 0.04, size=n_mtc).astype(np.float32)
+    if case != 'cfg4':
+        d = (np.round(d * 250) / 250).astype(np.float32)             # heavy exact ties, many values == 0.02
+        d[rs.randint(0, n_mtc, size=max(1, n_mtc // 50))] = np.nan
+    d[tmatches[0] == 0] = 0.001                                      # hypothesis 0 is the best of its pair
+    eng = E.Engine(0, max_batch=1)
+    ref = E.ransac_inliers(seeds[0], seeds[1], tmatches[0], tmatches[1], tmatches[2], d, 0.02, 3)
+    out = eng.ransac_inliers_dev(seeds[0], seeds[1], torch.from_numpy(tmatches).to(eng.device),
+                                 torch.from_numpy(d).to(eng.device), 0.02, 3)
+    assert len(ref['best_hypotheses']) > 0
+    for k in ('inlier_matches_cand1', 'inlier_matches_cand2', 'best_hypotheses'):
+        assert np.array_equal(ref[k], out[k]), k
+    eng.close()
+
+
 def test_ba_linearize_f64_and_lm_solve():
     """float64 linearisation on the device against the autograd oracle evaluated in float64 (1e-9 relative), and the
     device Cholesky solve against numpy's float64 solve of the same damped system."""

@@ -77,3 +77,37 @@ def test_sharded_equals_single_rank(tmp_path):
                        capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert 'rank0ok' in r.stdout and 'rank1ok' in r.stdout
+
+
+def _forward(eng, dev, seed=3, B=4):
+    gen = torch.Generator().manual_seed(seed)
+    crops = torch.rand((B, 3, 240, 320), generator=gen).to(dev)
+    renders = torch.rand((B, 3, 240, 320), generator=gen).to(dev)
+    return eng.net_forward(0, crops, renders)
+
+
+def test_two_handles_in_one_process_keep_their_own_state():
+    """Handles are independent (include/cosyb200.h): options set on one handle do not leak into another, and - with
+    two GPUs - a second handle on another device gets its own shared-memory opt-ins and SM count."""
+    from helpers import state_dict
+    from cosypose_b200.engine import Engine
+    a, b = Engine(0, max_batch=4), Engine(0, max_batch=4)
+    for e in (a, b):
+        e.load_pose_model(0, state_dict(0))
+    a.set_option('gemm_impl', 0)
+    a.set_option('xdw', 0)
+    ya1 = _forward(a, a.device)
+    yb = _forward(b, b.device)            # default options: tcgen05 3xFP16 + fused kernel
+    ya2 = _forward(a, a.device)
+    assert torch.equal(ya1, ya2)          # b's launches did not change a's configuration
+    assert not torch.equal(ya1, yb) and (ya1 - yb).abs().max() < 1e-4 * ya1.abs().max()   # raw head outputs, O(100)
+    if torch.cuda.device_count() >= 2:
+        c = Engine(1, max_batch=4)
+        c.load_pose_model(0, state_dict(0))
+        yc = _forward(c, c.device)
+        assert torch.equal(yb.cpu(), yc.cpu())      # same kernels, same inputs, another device
+        yb2 = _forward(b, b.device)
+        assert torch.equal(yb, yb2)
+        c.close()
+    a.close()
+    b.close()
