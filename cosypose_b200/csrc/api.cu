@@ -527,6 +527,7 @@ int cosyb200_create(cosyb200_handle** out, int device, int max_batch) {
     rc |= opt_in_smem(xdw::k_xdw<5, 2, 1, 64, 3>, 208 * 1024);
     rc |= opt_in_smem(xdw::k_xdw<5, 1, 2, 48, 5>, 208 * 1024);
     rc |= opt_in_smem(xdw::k_xdw<3, 2, 2, 48, 2>, 208 * 1024);
+    rc |= opt_in_smem(k_lm_solve<true>, LM_SMEM_MAX_N * (LM_SMEM_MAX_N + 1) / 2 * 8);
     rc |= opt_in_smem(k_roi_crop, (int)(CROP_SMEM_FLOATS * sizeof(float)));
     rc |= opt_in_smem(k_se_gate, 100 * 1024);
     rc |= opt_in_smem(k_dw_tile<5, 1, 40, 1>, 80 * 1024);
@@ -1364,7 +1365,10 @@ int cosyb200_lm_solve(cosyb200_handle* h, int n, const double* JtJ64, const doub
     h->lm_ws_elems = need;
   }
   LaunchScope ls(h, CAT_RANSAC, st);
-  k_lm_solve<<<1, LM_THREADS, 0, st>>>(n, JtJ64, Jte64, lambda, h->lm_ws, step, n_bad_pivots_dev);
+  if (n <= LM_SMEM_MAX_N)
+    k_lm_solve<true><<<1, LM_THREADS, (size_t)n * (n + 1) / 2 * 8, st>>>(n, JtJ64, Jte64, lambda, h->lm_ws, step, n_bad_pivots_dev);
+  else
+    k_lm_solve<false><<<1, LM_THREADS, 0, st>>>(n, JtJ64, Jte64, lambda, h->lm_ws, step, n_bad_pivots_dev);
   CB_LAUNCH_CHECK();
   return COSYB200_OK;
 }

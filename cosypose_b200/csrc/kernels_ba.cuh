@@ -372,39 +372,45 @@ __global__ void k_ba_loss_d(int n_res, const double* __restrict__ errors, double
 }
 
 // LM step h = (JtJ + lambda I)^-1 Jte (compute_lm_step, bundle_adjustment.py:216-222: pinverse of a positive
-// definite matrix) by a Cholesky factorisation in float64: ONE CTA, right-looking, the matrix lives in `A` (global,
-// L2 resident: n = 216 -> 373 KB), the current column in shared memory.  A pivot that is not positive (cannot happen
+// definite matrix) by a Cholesky factorisation in float64: ONE CTA, right-looking; the packed lower triangle lives in
+// shared memory when it fits (n <= 220: config 4 has n = 216 -> 187 KB), otherwise in `Ag` (global, L2 resident).  A pivot that is not positive (cannot happen
 // for J^T J + lambda I in exact arithmetic) is replaced by lambda and counted in *n_bad.
 constexpr int LM_THREADS = 1024;
 constexpr int LM_MAX_N = 2048;
+constexpr int LM_SMEM_MAX_N = 220;      // packed lower triangle in shared memory: n (n + 1) / 2 doubles <= 190 KB
+
+// SMEM: the lower triangle lives in dynamic shared memory (packed rows), otherwise in `Ag` (global, n x n)
+template <bool SMEM>
 __global__ void __launch_bounds__(LM_THREADS)
 k_lm_solve(int n, const double* __restrict__ JtJ, const double* __restrict__ Jte, double lambda,
-           double* __restrict__ A, float* __restrict__ step, int* __restrict__ n_bad) {
-  __shared__ double s_col[LM_MAX_N];
-  __shared__ double s_y[LM_MAX_N];
+           double* __restrict__ Ag, float* __restrict__ step, int* __restrict__ n_bad) {
+  extern __shared__ double s_tri[];
+  __shared__ double s_col[SMEM ? LM_SMEM_MAX_N : LM_MAX_N];
+  __shared__ double s_y[SMEM ? LM_SMEM_MAX_N : LM_MAX_N];
   __shared__ int s_bad;
   const int tid = threadIdx.x;
+  auto at = [&](int i, int j) -> double& {       // j <= i
+    if (SMEM) return s_tri[i * (i + 1) / 2 + j];
+    return Ag[(size_t)i * n + j];
+  };
   if (tid == 0) s_bad = 0;
   for (int idx = tid; idx < n * n; idx += LM_THREADS) {
     const int i = idx / n, j = idx % n;
-    A[idx] = JtJ[idx] + (i == j ? lambda : 0.0);
+    if (j <= i) at(i, j) = JtJ[idx] + (i == j ? lambda : 0.0);
   }
   __syncthreads();
   for (int k = 0; k < n; ++k) {
-    double akk = A[(size_t)k * n + k];
+    double akk = at(k, k);
     if (!(akk > 0.0)) { akk = lambda > 0.0 ? lambda : 1e-300; if (tid == 0) s_bad += 1; }
     const double d = sqrt(akk);
-    for (int i = k + tid; i < n; i += LM_THREADS) {
-      const double l = i == k ? d : A[(size_t)i * n + k] / d;
-      s_col[i] = l;
-    }
+    for (int i = k + tid; i < n; i += LM_THREADS) s_col[i] = i == k ? d : at(i, k) / d;
     __syncthreads();
-    for (int i = k + tid; i < n; i += LM_THREADS) A[(size_t)i * n + k] = s_col[i];   // L[:, k]
+    for (int i = k + tid; i < n; i += LM_THREADS) at(i, k) = s_col[i];   // L[:, k]
     // trailing update of the lower triangle: A[i][j] -= L[i][k] L[j][k], k < j <= i
     const int m = n - k - 1;
     for (int idx = tid; idx < m * m; idx += LM_THREADS) {
       const int i = k + 1 + idx / m, j = k + 1 + idx % m;
-      if (j <= i) A[(size_t)i * n + j] -= s_col[i] * s_col[j];
+      if (j <= i) at(i, j) -= s_col[i] * s_col[j];
     }
     __syncthreads();
   }
@@ -412,17 +418,17 @@ k_lm_solve(int n, const double* __restrict__ JtJ, const double* __restrict__ Jte
   for (int i = tid; i < n; i += LM_THREADS) s_y[i] = Jte[i];
   __syncthreads();
   for (int k = 0; k < n; ++k) {
-    const double yk = s_y[k] / A[(size_t)k * n + k];
+    const double yk = s_y[k] / at(k, k);
     __syncthreads();
     if (tid == 0) s_y[k] = yk;
-    for (int i = k + 1 + tid; i < n; i += LM_THREADS) s_y[i] -= A[(size_t)i * n + k] * yk;
+    for (int i = k + 1 + tid; i < n; i += LM_THREADS) s_y[i] -= at(i, k) * yk;
     __syncthreads();
   }
   for (int k = n - 1; k >= 0; --k) {
-    const double hk = s_y[k] / A[(size_t)k * n + k];
+    const double hk = s_y[k] / at(k, k);
     __syncthreads();
     if (tid == 0) s_y[k] = hk;
-    for (int i = tid; i < k; i += LM_THREADS) s_y[i] -= A[(size_t)k * n + i] * hk;
+    for (int i = tid; i < k; i += LM_THREADS) s_y[i] -= at(k, i) * hk;
     __syncthreads();
   }
   for (int i = tid; i < n; i += LM_THREADS) step[i] = (float)s_y[i];

@@ -4,6 +4,7 @@ PyTorch is used for device memory and streams only; every computation below is a
 libcosyb200.so.  Tensors must be fp32 / int32, contiguous and on the engine's CUDA device.
 """
 import ctypes
+import os
 from ctypes import c_char_p, c_int32, c_int64, c_void_p
 
 import numpy as np
@@ -39,6 +40,8 @@ class Engine:
         self.n_labels = 0
         self.s_max = 0
         self.loaded = [False, False]
+        if os.environ.get('COSYB200_GRAPH') == '0':      # profiling runs: plain launches instead of graph replay
+            self.set_option('graph', 0)
 
     def close(self):
         if getattr(self, '_h', None):
