@@ -283,26 +283,51 @@ def run_single_view(args, cfg, rank, local_rank, world):
     h_out = torch.empty((job.n, 4, 4), dtype=torch.float32).pin_memory()
     h2d = h_images.numel() * 4 + h_K.numel() * 4 + h_boxes.numel() * 4 + sum(v.numel() for v in h_views)
     d2h = h_out.numel() * 4
-    e_images = torch.zeros_like(d_images)
-    e_K, e_boxes = torch.empty_like(d_K), torch.empty_like(d_boxes)
-    e_views = [torch.empty(v.shape, dtype=torch.uint8, device=dev) for v in h_views]
-    e_rv = PreRenderedViews.from_chunks(e_views, BSZ)
-    e_det = tc.PandasTensorCollection(infos=infos, bboxes=e_boxes)
+    # Two sets of landing buffers and a copy stream: the inputs of step i+1 are uploaded while step i computes (what a
+    # serving loop does); every timed step still contains one full host->device copy of a step's inputs and one
+    # device->host read of its result.
+    class Landing:
+        def __init__(self):
+            self.images = torch.zeros_like(d_images)
+            self.K, self.boxes = torch.empty_like(d_K), torch.empty_like(d_boxes)
+            self.views = [torch.empty(v.shape, dtype=torch.uint8, device=dev) for v in h_views]
+            self.rv = PreRenderedViews.from_chunks(self.views, BSZ)
+            self.det = tc.PandasTensorCollection(infos=infos, bboxes=self.boxes)
+            self.ready, self.done = torch.cuda.Event(), torch.cuda.Event()
+            self.done.record()
+
+    sets = [Landing(), Landing()]
+    copy_stream = torch.cuda.Stream(device=dev)
+    e2e_state = {'i': 0}
+
+    def upload(s):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(s.done)                 # the step that last read these buffers has finished
+            s.images[job.f0:job.f1].copy_(h_images, non_blocking=True)
+            s.K.copy_(h_K, non_blocking=True)
+            s.boxes.copy_(h_boxes, non_blocking=True)
+            for dst, src in zip(s.views, h_views):
+                dst.copy_(src, non_blocking=True)
+            s.ready.record(copy_stream)
+
+    upload(sets[0])
 
     def step_e2e():
-        e_images[job.f0:job.f1].copy_(h_images, non_blocking=True)
-        e_K.copy_(h_K, non_blocking=True)
-        e_boxes.copy_(h_boxes, non_blocking=True)
-        for dst, src in zip(e_views, h_views):
-            dst.copy_(src, non_blocking=True)
-        e_rv.reset()
-        pred.coarse_model.renderer = e_rv
-        pred.refiner_model.renderer = e_rv
-        final, _ = pred.get_predictions(e_images, e_K, detections=e_det, n_coarse_iterations=c['n_coarse'],
+        i = e2e_state['i']
+        e2e_state['i'] = i + 1
+        s = sets[i % 2]
+        cur = torch.cuda.current_stream()
+        cur.wait_event(s.ready)
+        s.rv.reset()
+        pred.coarse_model.renderer = s.rv
+        pred.refiner_model.renderer = s.rv
+        final, _ = pred.get_predictions(s.images, s.K, detections=s.det, n_coarse_iterations=c['n_coarse'],
                                         n_refiner_iterations=c['n_refine'], shard=world > 1)
         poses = finish(final)
+        s.done.record(cur)
+        upload(sets[(i + 1) % 2])                           # next step's inputs, under this step's compute
         h_out.copy_(poses, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        cur.synchronize()                                   # the step's result is on the host
         return poses
 
     def barrier():
