@@ -63,6 +63,7 @@ _SIGS = {
     'cosyb200_ransac_inliers': ([c_int64, _P, _P, c_int64, _P, _P, _P, _P, c_float, c_int, _P, _P,
                                  POINTER(c_int64), _P, POINTER(c_int64)], c_int),
     'cosyb200_ransac_inliers_dev': ([_P, c_int64, c_int64, _P, c_int64, _P, _P, _P, _P, c_float, c_int, _P, _P, _P, _P, _P], c_int),
+    'cosyb200_pose_errors': ([_P, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P], c_int),
     'cosyb200_scatter_argmin': ([c_int64, _P, _P, c_int64, _P], c_int),
     'cosyb200_expand_ids_for_symmetry': ([c_int64, _P, _P, POINTER(c_int64), _P, _P], c_int),
 }

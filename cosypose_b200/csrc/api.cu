@@ -13,6 +13,7 @@
 #include "kernels_geometry.cuh"
 #include "kernels_ransac.cuh"
 #include "kernels_ba.cuh"
+#include "kernels_eval.cuh"
 #include "kernels_tc.cuh"
 #include "kernels_pw2.cuh"
 #include "kernels_xdw.cuh"
@@ -528,6 +529,7 @@ int cosyb200_create(cosyb200_handle** out, int device, int max_batch) {
     rc |= opt_in_smem(xdw::k_xdw<5, 1, 2, 48, 5>, 208 * 1024);
     rc |= opt_in_smem(xdw::k_xdw<3, 2, 2, 48, 2>, 208 * 1024);
     rc |= opt_in_smem(k_lm_solve<true>, LM_SMEM_MAX_N * (LM_SMEM_MAX_N + 1) / 2 * 8);
+    rc |= opt_in_smem(k_pose_errors, 16000 * 12);
     rc |= opt_in_smem(k_roi_crop, (int)(CROP_SMEM_FLOATS * sizeof(float)));
     rc |= opt_in_smem(k_se_gate, 100 * 1024);
     rc |= opt_in_smem(k_dw_tile<5, 1, 40, 1>, 80 * 1024);
@@ -1251,6 +1253,20 @@ int cosyb200_ba_linearize(cosyb200_handle* h, int n_cand, int n_obj, int n_view,
     k_ba_normal<<<grid, block, 0, st>>>(n_cand, n_pts, n_obj, n_view, cand_obj, cand_view, Jc, errors, JtJ, Jte);
     CB_LAUNCH_CHECK();
   }
+  return COSYB200_OK;
+}
+
+// ADD / ADD-S errors of n (prediction, ground truth) pairs (kernels_eval.cuh)
+int cosyb200_pose_errors(cosyb200_handle* h, int n, int n_points, const float* T_pred, const float* T_gt,
+                         const float* points, const int32_t* symmetric, float* dists, float* norm_avg,
+                         float* xyz_avg, float* tco_xyz, float* tco_norm, void* stream) {
+  CB_CHECK_ARG(h != nullptr && n >= 1 && n_points >= 1 && n_points <= 16000, "pose_errors: bad sizes (n_points <= 16000)");
+  CB_CHECK_ARG(T_pred && T_gt && points && norm_avg && xyz_avg && tco_xyz && tco_norm, "pose_errors: null pointer");
+  DeviceGuard guard(h->device);
+  LaunchScope ls(h, CAT_RANSAC, (cudaStream_t)stream);
+  k_pose_errors<<<n, EVAL_THREADS, (size_t)n_points * 12, (cudaStream_t)stream>>>(
+      n, n_points, T_pred, T_gt, points, symmetric, dists, norm_avg, xyz_avg, tco_xyz, tco_norm);
+  CB_LAUNCH_CHECK();
   return COSYB200_OK;
 }
 

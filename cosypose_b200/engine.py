@@ -378,6 +378,24 @@ class Engine:
         return dict(inlier_matches_cand1=o1[:no].cpu().numpy(), inlier_matches_cand2=o2[:no].cpu().numpy(),
                     best_hypotheses=ob[:nb].cpu().numpy())
 
+    def pose_errors(self, TXO_pred, TXO_gt, points, symmetric=None, return_dists=False):
+        """ADD (symmetric[b] == 0) / ADD-S (!= 0) errors of n pose pairs; points [n,P,3] are the model points of each
+        pair's label (reference: lib3d/distances.py:5-21, evaluation/meters/pose_meters.py:84-89)."""
+        n, P = points.shape[0], points.shape[1]
+        self._chk(TXO_pred, torch.float32, (n, 4, 4), 'TXO_pred')
+        self._chk(TXO_gt, torch.float32, (n, 4, 4), 'TXO_gt')
+        self._chk(points, torch.float32, (n, P, 3), 'points')
+        if symmetric is not None:
+            self._chk(symmetric, torch.int32, (n,), 'symmetric')
+        dists = self._new(n, P, 3) if return_dists else None
+        out = dict(norm_avg=self._new(n), xyz_avg=self._new(n, 3), TCO_xyz=self._new(n, 3), TCO_norm=self._new(n))
+        _lib.check(self._L.cosyb200_pose_errors(self._h, n, P, _ptr(TXO_pred), _ptr(TXO_gt), _ptr(points), _ptr(symmetric),
+                                                _ptr(dists), _ptr(out['norm_avg']), _ptr(out['xyz_avg']),
+                                                _ptr(out['TCO_xyz']), _ptr(out['TCO_norm']), self._stream()), 'pose_errors')
+        if return_dists:
+            out['dists'] = dists
+        return out
+
     def ba_linearize_f64(self, cand_TCO, cand_obj, cand_view, cand_label, TWO_9d, TCW_9d, K, points,
                          residuals_threshold=25.0, normal_equations=True):
         """ba_linearize evaluated in float64 on the device: JtJ / Jte / loss are float64 device tensors."""

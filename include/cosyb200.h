@@ -284,6 +284,15 @@ int cosyb200_ba_linearize_f64(cosyb200_handle* h, int n_cand, int n_obj, int n_v
 int cosyb200_lm_solve(cosyb200_handle* h, int n, const double* JtJ64_dev, const double* Jte64_dev, double lambda,
                       float* step_dev, int32_t* n_bad_pivots_dev, void* stream);
 
+/* ADD / ADD-S pose errors (reference: lib3d/distances.py:5-21 and the statistics of
+ * evaluation/meters/pose_meters.py:84-89).  T_pred, T_gt [n,4,4], points [n,P,3] (the label's model points per
+ * pair), symmetric [n] (0: ADD, else ADD-S with the first-minimum assignment of `dists_add_symmetric`; NULL = all ADD)
+ * -> dists [n,P,3] (may be NULL), norm_avg [n], xyz_avg [n,3], TCO_xyz [n,3], TCO_norm [n]. */
+int cosyb200_pose_errors(cosyb200_handle* h, int n, int n_points, const float* T_pred_dev,
+                         const float* T_gt_dev, const float* points_dev, const int32_t* symmetric_dev,
+                         float* dists_dev, float* norm_avg_dev, float* xyz_avg_dev, float* tco_xyz_dev,
+                         float* tco_norm_dev, void* stream);
+
 /* Index preconditions.  label ids and image ids of the single-view entry points (tco_init, prepare_iter, roi_crop,
  * refine_iter, refine_n) are clamped into their tables on the device, so a bad id cannot read out of bounds (its result
  * is meaningless).  The multiview entry points (ransac_models / ransac_score / symmetric_distance / ransac_inliers_dev /

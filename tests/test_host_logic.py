@@ -197,6 +197,24 @@ def test_sharded_predictor_gloo(tmp_path, nproc):
     assert all(f'rank{i}ok' in r.stdout for i in range(nproc))
 
 
+def test_bop_csv_round_trip(tmp_path):
+    from cosypose_b200.evaluation import bop_io
+    from cosypose_b200.utils import tensor_collection as tc
+    gen = torch.Generator().manual_seed(1)
+    poses = torch.eye(4).repeat(3, 1, 1)
+    poses[:, :3, 3] = torch.rand((3, 3), generator=gen)
+    infos = pd.DataFrame(dict(scene_id=[1, 1, 2], view_id=[0, 3, 7], label=['obj_000004', 'obj_000011', 'obj_000004'],
+                              score=[0.9, 0.5, 1.0]))
+    p = tmp_path / 'r.csv'
+    bop_io.tc_to_csv(tc.PandasTensorCollection(infos=infos, poses=poses), p)
+    txt = p.read_text().splitlines()
+    assert txt[0] == 'scene_id,im_id,obj_id,score,R,t,time' and len(txt) == 4
+    assert txt[1].startswith('1,0,4,0.9,1.0 0.0 0.0 0.0 1.0 0.0 0.0 0.0 1.0,') and txt[1].endswith(',-1.0')
+    back = bop_io.read_csv_candidates(p)
+    assert list(back.infos['label']) == list(infos['label']) and list(back.infos['view_id']) == [0, 3, 7]
+    assert (back.poses - poses).abs().max() < 1e-6
+
+
 def test_product_never_imports_the_oracle():
     """The product package must not import, call or link anything under oracle/ (checker only)."""
     for p in (ROOT / 'cosypose_b200').rglob('*.py'):
