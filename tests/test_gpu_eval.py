@@ -62,6 +62,22 @@ def test_add_and_adds_errors():
     eng.close()
 
 
+def test_add_distances_vs_reference_golden(golden_dir):
+    """dists_add / dists_add_symmetric against the outputs of the reference's own functions (add_distances.npz)."""
+    from cosypose_b200.engine import Engine
+    from cosypose_b200.lib3d import distances
+    g = np.load(golden_dir / 'add_distances.npz')
+    eng = Engine(0, max_batch=1)
+    dev = eng.device
+    Tp, Tg, pts = (torch.from_numpy(g[k]).to(dev) for k in ('T_pred', 'T_gt', 'points'))
+    d = distances.dists_add(Tp, Tg, pts, engine=eng).cpu().numpy()
+    assert np.abs(d - g['dists_add']).max() < 1e-6
+    ds = distances.dists_add_symmetric(Tp, Tg, pts, engine=eng).cpu().numpy()
+    assert np.abs(np.linalg.norm(ds, axis=-1) - np.linalg.norm(g['dists_add_symmetric'], axis=-1)).max() < 1e-6
+    assert (np.abs(ds - g['dists_add_symmetric']).max(-1) < 1e-6).mean() > 0.999     # fp32 near-ties of the argmin
+    eng.close()
+
+
 def test_hypothesis_queue_equals_per_group_calls():
     """Three view groups refined in one batched call give each group exactly what a call of its own gives."""
     from cosypose_b200.evaluation.hypothesis_queue import HypothesisQueue
