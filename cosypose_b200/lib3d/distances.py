@@ -1,5 +1,5 @@
 """ADD / ADD-S distances with the reference's function signatures (reference: cosypose/lib3d/distances.py:5-21),
-computed by `cosyb200_pose_errors` (one CTA per pose pair, the ground-truth points in shared memory) instead of the
+computed by `cosyb200_pose_errors` (one CTA per pose pair, the predicted points in shared memory) instead of the
 [n, P, P, 3] difference tensor, plus the error statistics of evaluation/meters/pose_meters.py:84-89 in the same pass."""
 import torch
 
@@ -25,7 +25,7 @@ def dists_add(TXO_pred, TXO_gt, points, engine=None):
 
 
 def dists_add_symmetric(TXO_pred, TXO_gt, points, engine=None):
-    """[n, P, 3]: for every predicted point the difference to its closest ground-truth point (first minimum)."""
+    """[n, P, 3]: for every ground-truth point the difference to its closest predicted point (first minimum)."""
     eng = _engine_for(TXO_pred, engine)
     sym = torch.ones(TXO_pred.shape[0], dtype=torch.int32, device=TXO_pred.device)
     return eng.pose_errors(TXO_pred.float().contiguous(), TXO_gt.float().contiguous(), points.float().contiguous(),

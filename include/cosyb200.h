@@ -286,7 +286,7 @@ int cosyb200_lm_solve(cosyb200_handle* h, int n, const double* JtJ64_dev, const 
 
 /* ADD / ADD-S pose errors (reference: lib3d/distances.py:5-21 and the statistics of
  * evaluation/meters/pose_meters.py:84-89).  T_pred, T_gt [n,4,4], points [n,P,3] (the label's model points per
- * pair), symmetric [n] (0: ADD, else ADD-S with the first-minimum assignment of `dists_add_symmetric`; NULL = all ADD)
+ * pair), symmetric [n] (0: ADD, else ADD-S: every ground-truth point against its closest predicted point, first minimum, as `dists_add_symmetric`; NULL = all ADD)
  * -> dists [n,P,3] (may be NULL), norm_avg [n], xyz_avg [n,3], TCO_xyz [n,3], TCO_norm [n]. */
 int cosyb200_pose_errors(cosyb200_handle* h, int n, int n_points, const float* T_pred_dev,
                          const float* T_gt_dev, const float* points_dev, const int32_t* symmetric_dev,

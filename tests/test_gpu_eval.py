@@ -18,11 +18,13 @@ def _ref_add(Tp, Tg, pts):          # lib3d/distances.py:5-9
     return _transform(Tg, pts) - _transform(Tp, pts)
 
 
-def _ref_adds(Tp, Tg, pts):         # lib3d/distances.py:12-21
+def _ref_adds(Tp, Tg, pts):         # lib3d/distances.py:12-21, line by line
     a, b = _transform(Tp, pts), _transform(Tg, pts)
-    d = b.unsqueeze(1) - a.unsqueeze(2)                  # [n, pred j, gt i, 3]
-    assign = (d ** 2).sum(-1).argmin(dim=2)
-    return torch.gather(d, 2, assign[..., None, None].expand(-1, -1, 1, 3)).squeeze(2)
+    d = b.unsqueeze(1) - a.unsqueeze(2)                  # [n, pred j, gt i, 3] = gt_i - pred_j
+    assign = (d ** 2).sum(-1).argmin(dim=1)              # over the predicted points, for every ground-truth point
+    ids_row = torch.arange(d.shape[0]).unsqueeze(1).repeat(1, d.shape[1])
+    ids_col = torch.arange(d.shape[1]).unsqueeze(0).repeat(d.shape[0], 1)
+    return d[ids_row, assign, ids_col]
 
 
 def test_add_and_adds_errors():
