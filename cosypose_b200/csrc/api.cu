@@ -363,8 +363,8 @@ static int net_forward(cosyb200_handle* h, int slot, int B, const float* crops, 
   {
     dim3 grid(RENDER_W / 2 / STEM_TX, RENDER_H / 2 / STEM_TY, B), block(STEM_TX, STEM_TY);
     LaunchScope ls(h, CAT_STEM, st);
-    if (render_u8) k_stem<true><<<grid, block, 0, st>>>(crops, renders, m.stem_w, m.stem_bias, h->act[0]);
-    else k_stem<false><<<grid, block, 0, st>>>(crops, renders, m.stem_w, m.stem_bias, h->act[0]);
+    if (render_u8) k_stem<true><<<grid, block, 0, st>>>(crops, renders, m.stem_host, h->act[0]);
+    else k_stem<false><<<grid, block, 0, st>>>(crops, renders, m.stem_host, h->act[0]);
     CB_LAUNCH_CHECK();
   }
   int cur = 0;
@@ -655,6 +655,10 @@ int cosyb200_load_pose_model(cosyb200_handle* h, int slot, int n, const char* co
             tmp[(t * IN_CH + ci) * STEM_OUT + co] = W[((size_t)co * IN_CH + ci) * 9 + t] * scale[co];
     rc |= upload(m, &m.stem_w, tmp);
     rc |= upload(m, &m.stem_bias, shift);
+    if (tmp.size() == 54 * STEM_OUT && shift.size() >= (size_t)STEM_OUT) {
+      memcpy(m.stem_host.w, tmp.data(), sizeof(m.stem_host.w));
+      memcpy(m.stem_host.bias, shift.data(), sizeof(m.stem_host.bias));
+    }
   }
   for (size_t i = 0; i < h->blocks.size() && !rc; ++i) {
     const BlockSpec& b = h->blocks[i];

@@ -71,10 +71,18 @@ struct BlockWeights {
   float proj_p2_inv = 1.f;
 };
 
+// Stem weights travel as a kernel PARAMETER (constant bank): every FFMA of the stem takes its weight straight from
+// c[0x0][imm], no shared-memory read (8.8 KB of the 32 KB parameter space).
+struct StemWeights {
+  float w[54][40];   // (ky, kx, ci) major, BN scale folded
+  float bias[40];
+};
+
 struct PoseModel {
   bool loaded = false;
   float* stem_w = nullptr;     // [54][40]: (ky,kx,ci) major, BN scale folded
   float* stem_bias = nullptr;  // [40]
+  StemWeights stem_host;       // the same, host copy passed by value at every stem launch
   std::vector<BlockWeights> blocks;
   float* head_nk = nullptr;    // [1536][384]
   float* head_kn = nullptr;    // [384][1536]

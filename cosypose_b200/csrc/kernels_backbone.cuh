@@ -41,16 +41,14 @@ static_assert(IN_CH * STEM_IH * STEM_IWP + 54 * STEM_CO <= STEM_SMEM, "stem smem
 // hands over before `.float() / 255` (rendering/bullet_batch_renderer.py:70-83); converted here.
 template <bool U8>
 __global__ void __launch_bounds__(STEM_TX* STEM_TY)
-k_stem(const float* __restrict__ crops, const void* __restrict__ renders_any,
-       const float* __restrict__ w /*[54][40]*/, const float* __restrict__ bias, float* __restrict__ out) {
+k_stem(const float* __restrict__ crops, const void* __restrict__ renders_any, const __grid_constant__ StemWeights wts,
+       float* __restrict__ out) {
   constexpr int H = RENDER_H, W = RENDER_W, HO = H / 2, WO = W / 2;
   __shared__ __align__(16) float smem[STEM_SMEM];
   float* s_in = smem;                                // [6][17][66]
-  float* s_w = smem + IN_CH * STEM_IH * STEM_IWP;    // [54][40]
   const int b = blockIdx.z;
   const int ox0 = blockIdx.x * STEM_TX, oy0 = blockIdx.y * STEM_TY;
   const int tid = threadIdx.y * STEM_TX + threadIdx.x;
-  for (int i = tid; i < 54 * STEM_CO; i += STEM_TX * STEM_TY) s_w[i] = w[i];
   for (int i = tid; i < IN_CH * STEM_IH * STEM_IW; i += STEM_TX * STEM_TY) {
     int c = i / (STEM_IH * STEM_IW), r = i % (STEM_IH * STEM_IW);
     int iy = r / STEM_IW, ix = r % STEM_IW;
@@ -74,34 +72,29 @@ k_stem(const float* __restrict__ crops, const void* __restrict__ renders_any,
 #pragma unroll
   for (int i = 0; i < STEM_CO; ++i) acc[i] = 0.f;
   const int tx = threadIdx.x, ty = threadIdx.y;
-#pragma unroll 1
+  // fully unrolled: every weight is a constant-bank operand of its FFMA (the shared-memory pipe was the co-bottleneck
+  // with 10 broadcast LDS.128 per 40 FFMA: profiles/r02_ncu_full_summary.csv, 54 % issue-active)
+#pragma unroll
   for (int c = 0; c < IN_CH; ++c) {
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
 #pragma unroll
       for (int kx = 0; kx < 3; ++kx) {
-        float v = s_in[(c * STEM_IH + 2 * ty + ky) * STEM_IWP + 2 * tx + kx];
-        const float4* wr = reinterpret_cast<const float4*>(s_w + ((ky * 3 + kx) * IN_CH + c) * STEM_CO);
+        const float v = s_in[(c * STEM_IH + 2 * ty + ky) * STEM_IWP + 2 * tx + kx];
 #pragma unroll
-        for (int q = 0; q < STEM_CO / 4; ++q) {
-          float4 ww = wr[q];
-          acc[4 * q + 0] = fmaf(v, ww.x, acc[4 * q + 0]);
-          acc[4 * q + 1] = fmaf(v, ww.y, acc[4 * q + 1]);
-          acc[4 * q + 2] = fmaf(v, ww.z, acc[4 * q + 2]);
-          acc[4 * q + 3] = fmaf(v, ww.w, acc[4 * q + 3]);
-        }
+        for (int q = 0; q < STEM_CO; ++q) acc[q] = fmaf(v, wts.w[(ky * 3 + kx) * IN_CH + c][q], acc[q]);
       }
     }
   }
-  __syncthreads();  // everyone is done with s_in / s_w: reuse as the output staging tile
+  __syncthreads();  // everyone is done with s_in: reuse as the output staging tile
   float4* s_out = reinterpret_cast<float4*>(smem);
 #pragma unroll
   for (int q = 0; q < STEM_CO / 4; ++q) {
     float4 o;
-    o.x = swishf(acc[4 * q + 0] + __ldg(bias + 4 * q + 0));
-    o.y = swishf(acc[4 * q + 1] + __ldg(bias + 4 * q + 1));
-    o.z = swishf(acc[4 * q + 2] + __ldg(bias + 4 * q + 2));
-    o.w = swishf(acc[4 * q + 3] + __ldg(bias + 4 * q + 3));
+    o.x = swishf(acc[4 * q + 0] + wts.bias[4 * q + 0]);
+    o.y = swishf(acc[4 * q + 1] + wts.bias[4 * q + 1]);
+    o.z = swishf(acc[4 * q + 2] + wts.bias[4 * q + 2]);
+    o.w = swishf(acc[4 * q + 3] + wts.bias[4 * q + 3]);
     s_out[tid * (STEM_CO / 4) + q] = o;
   }
   __syncthreads();
