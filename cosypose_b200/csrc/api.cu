@@ -415,11 +415,19 @@ static int net_forward(cosyb200_handle* h, int slot, int B, const float* crops, 
                                            1.0f / float(b.hout * b.wout), w.se_r_b, w.se_e_w, w.se_e_b, h->gate);
     } else {
       LaunchScope ls(h, CAT_SE, st);
-      const dim3 se_grid((B + SE_IMGS - 1) / SE_IMGS, b.cexp >= 1024 ? 8 : (b.cexp >= 256 ? 4 : 1));
-      const size_t se_smem = (size_t)SE_IMGS * (b.cexp + b.cse) * sizeof(float);
-      k_se_gate<<<se_grid, SE_THREADS, se_smem, st>>>(B, h->pool_partial, p.tiles, b.cexp, b.cse,
-                                                      1.0f / float(b.hout * b.wout), w.se_r_w, w.se_r_b, w.se_e_w,
-                                                      w.se_e_b, h->gate);
+      if (b.cexp <= 288) {
+        const dim3 se_grid((B + SE_IMGS_SMALL - 1) / SE_IMGS_SMALL, 1);
+        const size_t se_smem = (size_t)SE_IMGS_SMALL * (b.cexp + b.cse) * sizeof(float);
+        k_se_gate<SE_IMGS_SMALL><<<se_grid, SE_THREADS, se_smem, st>>>(B, h->pool_partial, p.tiles, b.cexp, b.cse,
+                                                                     1.0f / float(b.hout * b.wout), w.se_r_w, w.se_r_b,
+                                                                     w.se_e_w, w.se_e_b, h->gate);
+      } else {
+        const dim3 se_grid((B + SE_IMGS - 1) / SE_IMGS, b.cexp >= 1024 ? 8 : 4);
+        const size_t se_smem = (size_t)SE_IMGS * (b.cexp + b.cse) * sizeof(float);
+        k_se_gate<SE_IMGS><<<se_grid, SE_THREADS, se_smem, st>>>(B, h->pool_partial, p.tiles, b.cexp, b.cse,
+                                                               1.0f / float(b.hout * b.wout), w.se_r_w, w.se_r_b, w.se_e_w,
+                                                               w.se_e_b, h->gate);
+      }
     }
     CB_LAUNCH_CHECK();
     if ((int)i == h->dump_block) {
@@ -531,7 +539,7 @@ int cosyb200_create(cosyb200_handle** out, int device, int max_batch) {
     rc |= opt_in_smem(k_lm_solve<true>, LM_SMEM_MAX_N * (LM_SMEM_MAX_N + 1) / 2 * 8);
     rc |= opt_in_smem(k_pose_errors, 16000 * 12);
     rc |= opt_in_smem(k_roi_crop, (int)(CROP_SMEM_FLOATS * sizeof(float)));
-    rc |= opt_in_smem(k_se_gate, 100 * 1024);
+    rc |= opt_in_smem(k_se_gate<SE_IMGS>, 100 * 1024);
     rc |= opt_in_smem(k_dw_tile<5, 1, 40, 1>, 80 * 1024);
     rc |= opt_in_smem(k_dw_tile<3, 2, 20, 1>, 80 * 1024);
     rc |= opt_in_smem(k_dw_tile<3, 1, 20, 1>, 80 * 1024);

@@ -384,8 +384,10 @@ k_dwconv_roll(const float* __restrict__ in, const float* __restrict__ w /*[KS*KS
 // expand weight transposed to [Cse][C] so that the last stage reads contiguously.
 // dynamic smem: SE_IMGS * (C + Cse) floats.
 constexpr int SE_THREADS = 1024;
-constexpr int SE_IMGS = 8;
+constexpr int SE_IMGS = 8;       // wide blocks: a CTA serves 8 hypotheses so that each FC weight read from L2 is used 8 times
+constexpr int SE_IMGS_SMALL = 2; // blocks 0-8 (C <= 288, tiny FCs, up to 100 tile partials per channel): 4x the CTAs instead
 
+template <int SE_IMGS>
 __global__ void __launch_bounds__(SE_THREADS)
 k_se_gate(int B, const float* __restrict__ partial, int tiles_per_img, int C, int Cse, float inv_hw,
           const float* __restrict__ wr, const float* __restrict__ br, const float* __restrict__ we_t,
