@@ -367,28 +367,45 @@ k_pw2(const float* __restrict__ A, const __half* __restrict__ Wpk, const float* 
       }
     } else {
       // ---------------------------------------------------------------- raw loaders (A rows + gate rows)
+      // The two loader warps were the slowest role (in-kernel trace: ~1500 cycles per item against ~1070 for a
+      // converter group and ~960 for the six MMAs): ptxas spent ~25 instructions of 64-bit address arithmetic and
+      // predicate logic on each of the 16 cp.async of an item.  Row offsets (32-bit, relative to the tile) and the
+      // row-valid mask are therefore computed once per tile; a stage adds one 64-bit base.
       const int lt = tid - RAW_WARP0 * 32;
       const int r0 = lt >> 3, kc = lt & 7;                  // chunk kc of rows r0, r0 + 8, ..., r0 + 120
-      const float* a_thr = A + (size_t)r0 * K + kc * 4;
       const uint32_t dst_thr = raw_base + r0 * RAW_ROW_BYTES + kc * 16;
       const int n_imgs = (M + rows_per_img - 1) / rows_per_img;
       int s = 0, m0 = m_first * BM, img0 = 0;
+      uint32_t roff[16];
+      uint32_t vmask = 0;
+      const char* tile_base = reinterpret_cast<const char*>(A);
       for (int i = 0; i < n_items; ++i) {
         const int rslot = i % RAW_DEPTH;
         const int k0 = s * BK;
-        if (GATE && s == 0) img0 = m0 / rows_per_img;
+        if (s == 0) {
+          if (GATE) img0 = m0 / rows_per_img;
+          tile_base = reinterpret_cast<const char*>(A + (size_t)m0 * K + kc * 4);
+          vmask = 0;
+#pragma unroll
+          for (int it = 0; it < 16; ++it) {
+            const bool ok = m0 + r0 + 8 * it < M;
+            roff[it] = ok ? (uint32_t)((r0 + 8 * it) * K) * 4u : 0u;
+            vmask |= (ok ? 1u : 0u) << it;
+          }
+        }
         if (i >= RAW_DEPTH) mbar_wait_warp(rawEmpty(rslot), ((i / RAW_DEPTH) - 1) & 1);
-        const bool kok = k0 + kc * 4 < K;
-        const float* src = a_thr + (size_t)m0 * K + k0;
+        const uint32_t kmask = k0 + kc * 4 < K ? vmask : 0u;
+        const char* src = tile_base + (size_t)k0 * 4;
         const uint32_t dst = dst_thr + rslot * RAW_STAGE_BYTES;
 #pragma unroll
         for (int it = 0; it < 16; ++it) {
-          const bool ok = kok && m0 + r0 + 8 * it < M;
-          cp_async16(dst + it * 8 * RAW_ROW_BYTES, ok ? (const void*)(src + (size_t)it * 8 * K) : (const void*)A, ok);
+          const uint32_t n = ((kmask >> it) & 1u) * 16u;     // src-size 0 -> the 16 destination bytes are zero filled
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + it * 8 * RAW_ROW_BYTES),
+                       "l"(src + roff[it]), "r"(n) : "memory");
         }
         if (GATE && gate_smem && lt < GATE_IMGS * 8) {
           const int img = img0 + r0;                        // r0 = lt / 8 = image within the tile here
-          const bool ok = kok && img < n_imgs;
+          const bool ok = k0 + kc * 4 < K && img < n_imgs;
           cp_async16(raw_base + rslot * RAW_STAGE_BYTES + RAW_GATE_OFF + lt * 16,
                      ok ? (const void*)(gate + (size_t)img * K + k0 + kc * 4) : (const void*)A, ok);
         }
