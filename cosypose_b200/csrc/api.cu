@@ -18,6 +18,7 @@
 #include "kernels_pw2.cuh"
 #include "kernels_xdw.cuh"
 #include "kernels_dwtile.cuh"
+#include "kernels_raster.cuh"
 
 namespace cosyb {
 
@@ -592,7 +593,8 @@ int cosyb200_destroy(cosyb200_handle* h) {
   free_model(h->models[1]);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   void* ptrs[] = {h->act[0], h->act[1], h->buf_e, h->buf_d, h->pool_partial, h->gate, h->crops, h->pose9,
-                  h->pts_sampled, h->sym, h->n_sym, h->aabb, h->io_buf, h->ba_ws, h->lm_ws, h->vote_ws};
+                  h->pts_sampled, h->sym, h->n_sym, h->aabb, h->io_buf, h->ba_ws, h->lm_ws, h->vote_ws,
+                  h->r_verts, h->r_colors, h->r_faces, h->r_face_off, h->r_zbuf, h->r_frames, h->r_big_cnt, h->r_big_list};
   for (void* p : ptrs) if (p) cudaFree(p);
   delete h;
   return COSYB200_OK;
@@ -863,6 +865,82 @@ int cosyb200_update_pose(cosyb200_handle* h, int B, const float* TCO_in, const f
   return COSYB200_OK;
 }
 
+// ---- device rasteriser (kernels_raster.cuh) ----------------------------------------------------------------
+int cosyb200_set_render_meshes(cosyb200_handle* h, int n_labels, int64_t n_vertices, const float* vertices,
+                               const float* colors, int64_t n_faces, const int32_t* faces, const int32_t* face_offsets) {
+  CB_CHECK_ARG(h != nullptr, "set_render_meshes: null handle");
+  CB_CHECK_ARG(n_labels >= 1 && n_vertices >= 1 && n_faces >= 1 && vertices && colors && faces && face_offsets,
+               "set_render_meshes: bad tables");
+  CB_CHECK_ARG(n_vertices < (1ll << 31) && n_faces < (1ll << 31), "set_render_meshes: more than 2^31 vertices or faces");
+  CB_CHECK_ARG(face_offsets[0] == 0 && face_offsets[n_labels] == n_faces, "set_render_meshes: face_offsets must run 0..n_faces");
+  int max_faces = 0;
+  for (int l = 0; l < n_labels; ++l) {
+    CB_CHECK_ARG(face_offsets[l + 1] >= face_offsets[l], "set_render_meshes: face_offsets must not decrease");
+    max_faces = std::max(max_faces, face_offsets[l + 1] - face_offsets[l]);
+  }
+  for (int64_t i = 0; i < 3 * n_faces; ++i)
+    CB_CHECK_ARG(faces[i] >= 0 && faces[i] < n_vertices, "set_render_meshes: face %lld names vertex %d of %lld",
+                 (long long)(i / 3), faces[i], (long long)n_vertices);
+  DeviceGuard guard(h->device);
+  clear_graphs(h);
+  h->model_epoch += 1;
+  for (void* p : {(void*)h->r_verts, (void*)h->r_colors, (void*)h->r_faces, (void*)h->r_face_off}) if (p) cudaFree(p);
+  h->r_verts = h->r_colors = nullptr; h->r_faces = h->r_face_off = nullptr;
+  h->r_labels = 0;
+  CB_CUDA(cudaMalloc((void**)&h->r_verts, (size_t)n_vertices * 12));
+  CB_CUDA(cudaMemcpy(h->r_verts, vertices, (size_t)n_vertices * 12, cudaMemcpyHostToDevice));
+  CB_CUDA(cudaMalloc((void**)&h->r_colors, (size_t)n_vertices * 12));
+  CB_CUDA(cudaMemcpy(h->r_colors, colors, (size_t)n_vertices * 12, cudaMemcpyHostToDevice));
+  CB_CUDA(cudaMalloc((void**)&h->r_faces, (size_t)n_faces * 12));
+  CB_CUDA(cudaMemcpy(h->r_faces, faces, (size_t)n_faces * 12, cudaMemcpyHostToDevice));
+  CB_CUDA(cudaMalloc((void**)&h->r_face_off, (size_t)(n_labels + 1) * 4));
+  CB_CUDA(cudaMemcpy(h->r_face_off, face_offsets, (size_t)(n_labels + 1) * 4, cudaMemcpyHostToDevice));
+  if (!h->r_zbuf) CB_CUDA(cudaMalloc((void**)&h->r_zbuf, (size_t)h->max_batch * RENDER_H * RENDER_W * 8));
+  if (!h->r_frames) CB_CUDA(cudaMalloc((void**)&h->r_frames, (size_t)h->max_batch * RENDER_H * RENDER_W * 3));
+  if (!h->r_big_cnt) CB_CUDA(cudaMalloc((void**)&h->r_big_cnt, (size_t)h->max_batch * 4));
+  if (h->r_big_list) { cudaFree(h->r_big_list); h->r_big_list = nullptr; }
+  CB_CUDA(cudaMalloc((void**)&h->r_big_list, (size_t)h->max_batch * max_faces * 4));
+  h->r_labels = n_labels;
+  h->r_max_faces = max_faces;
+  return COSYB200_OK;
+}
+
+static int launch_render(cosyb200_handle* h, int B, const int32_t* label_ids, const float* TCO, const float* K,
+                         void* out, int out_u8, cudaStream_t st) {
+  if (h->r_labels == 0) { set_error("render: render meshes not set (cosyb200_set_render_meshes)"); return COSYB200_ESTATE; }
+  const size_t npix = (size_t)B * RENDER_H * RENDER_W;
+  static_assert(RENDER_H % raster::TILE == 0 && RENDER_W % raster::TILE == 0, "resolve tiles must cover the view");
+  CB_CUDA(cudaMemsetAsync(h->r_zbuf, 0xff, npix * 8, st));
+  CB_CUDA(cudaMemsetAsync(h->r_big_cnt, 0, (size_t)B * 4, st));
+  {
+    LaunchScope ls(h, CAT_RENDER, st);
+    const dim3 grid((h->r_max_faces + raster::RT_THREADS - 1) / raster::RT_THREADS, B);
+    raster::k_raster_tris<<<grid, raster::RT_THREADS, 0, st>>>(h->r_verts, h->r_faces, h->r_face_off, h->r_labels, label_ids,
+                                                               TCO, K, h->r_zbuf, h->r_big_cnt, h->r_big_list,
+                                                               h->r_max_faces);
+  }
+  {
+    LaunchScope ls(h, CAT_RENDER, st);
+    const dim3 grid(RENDER_W / raster::TILE, RENDER_H / raster::TILE, B);
+    if (out_u8)
+      raster::k_raster_resolve<true><<<grid, 256, 0, st>>>(h->r_verts, h->r_colors, h->r_faces, TCO, K, h->r_zbuf,
+                                                           h->r_big_cnt, h->r_big_list, h->r_max_faces, out);
+    else
+      raster::k_raster_resolve<false><<<grid, 256, 0, st>>>(h->r_verts, h->r_colors, h->r_faces, TCO, K, h->r_zbuf,
+                                                            h->r_big_cnt, h->r_big_list, h->r_max_faces, out);
+  }
+  CB_LAUNCH_CHECK();
+  return COSYB200_OK;
+}
+
+int cosyb200_render(cosyb200_handle* h, int B, const int32_t* label_ids, const float* TCO, const float* K, void* out,
+                    int out_u8, void* stream) {
+  if (int rc = check_batch(h, B, "render")) return rc;
+  CB_CHECK_ARG(label_ids && TCO && K && out, "render: null argument");
+  DeviceGuard guard(h->device);
+  return launch_render(h, B, label_ids, TCO, K, out, out_u8, (cudaStream_t)stream);
+}
+
 int cosyb200_refine_iter(cosyb200_handle* h, int slot, int B, const float* images, int n_images,
                          int img_h, int img_w, const int32_t* im_ids, const float* boxes_crop,
                          const void* renders, int render_u8, const float* K_crop, const float* TCO_in,
@@ -883,6 +961,7 @@ int cosyb200_refine_n(cosyb200_handle* h, int slot, int B, int n_iter, const flo
                       float* pose9, void* stream) {
   if (int rc = check_batch(h, B, "refine_n")) return rc;
   CB_CHECK_ARG(n_iter >= 1, "refine_n: n_iter %d", n_iter);
+  if (!renders && h->r_labels == 0) { set_error("refine_n: no views given and no render meshes set"); return COSYB200_ESTATE; }
   struct Io { const int32_t* im_ids; const float* K; const int32_t* label_ids; const float* TCO_in;
               float *TCO_out, *K_crop, *boxes_rend, *boxes_crop, *pose9; };
   auto run = [&](void* st, const Io& io) -> int {
@@ -891,11 +970,18 @@ int cosyb200_refine_n(cosyb200_handle* h, int slot, int B, int n_iter, const flo
       int rc = cosyb200_prepare_iter(h, B, img_h, img_w, io.K, tin, io.label_ids, io.boxes_rend + (size_t)n * B * 4,
                                      io.boxes_crop + (size_t)n * B * 4, io.K_crop + (size_t)n * B * 9, st);
       if (rc) return rc;
+      const void* views = (const char*)renders + (size_t)n * B * 3 * RENDER_H * RENDER_W * (render_u8 ? 1 : 4);
+      int views_u8 = render_u8;
+      if (!renders) {   // no views handed in: rasterise the hypotheses at their current poses (pose.py:100-102)
+        DeviceGuard guard(h->device);
+        rc = launch_render(h, B, io.label_ids, tin, io.K_crop + (size_t)n * B * 9, h->r_frames, 1, (cudaStream_t)st);
+        if (rc) return rc;
+        views = h->r_frames;
+        views_u8 = 1;
+      }
       rc = cosyb200_refine_iter(h, slot, B, images, n_images, img_h, img_w, io.im_ids,
-                                io.boxes_crop + (size_t)n * B * 4,
-                                (const char*)renders + (size_t)n * B * 3 * RENDER_H * RENDER_W * (render_u8 ? 1 : 4),
-                                render_u8, io.K_crop + (size_t)n * B * 9, tin, io.pose9 + (size_t)n * B * POSE_DIM,
-                                io.TCO_out + (size_t)n * B * 16, st);
+                                io.boxes_crop + (size_t)n * B * 4, views, views_u8, io.K_crop + (size_t)n * B * 9, tin,
+                                io.pose9 + (size_t)n * B * POSE_DIM, io.TCO_out + (size_t)n * B * 16, st);
       if (rc) return rc;
     }
     return COSYB200_OK;

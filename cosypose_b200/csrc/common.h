@@ -117,9 +117,19 @@ struct cosyb200_handle {
   float* gate = nullptr;               // [B][cexp_max]
   float* crops = nullptr;              // [B][3][240][320]
   float* pose9 = nullptr;              // [B][9] scratch
+  // device rasteriser (cosyb200_set_render_meshes / cosyb200_render; kernels_raster.cuh)
+  float* r_verts = nullptr;            // [n_vertices][3] object frame
+  float* r_colors = nullptr;           // [n_vertices][3] in [0, 1]
+  int32_t* r_faces = nullptr;          // [n_faces][3] vertex ids
+  int32_t* r_face_off = nullptr;       // [r_labels + 1] first face of every label
+  int r_labels = 0, r_max_faces = 0;
+  unsigned long long* r_zbuf = nullptr;   // [max_batch][240][320] depth / triangle keys
+  int* r_big_cnt = nullptr;               // [max_batch] triangles too large for a warp, per hypothesis
+  int* r_big_list = nullptr;              // [max_batch][r_max_faces] their face ids
+  unsigned char* r_frames = nullptr;      // [max_batch][240][320][3] views of the current iteration (refine_n without views)
   size_t act_elems = 0, e_elems = 0, d_elems = 0, partial_elems = 0;
   // launch accounting / optional per-category device timing (cosyb200_profile_*)
-  static constexpr int N_CAT = 10;
+  static constexpr int N_CAT = 11;
   int64_t launches[N_CAT] = {0};
   double cat_ms[N_CAT] = {0};
   static constexpr int N_BLK = 32;     // per-MBConv-block split of cat_ms (index 31: outside the blocks)
@@ -162,7 +172,7 @@ struct cosyb200_handle {
 
 namespace cosyb {
 enum Cat { CAT_GEOMETRY = 0, CAT_CROP, CAT_STEM, CAT_EXPAND, CAT_DW, CAT_SE, CAT_PROJECT, CAT_HEAD,
-           CAT_POOL_FC, CAT_RANSAC };
+           CAT_POOL_FC, CAT_RANSAC, CAT_RENDER };
 int prof_resolve(cosyb200_handle* h);
 // Scope object: counts the launch and, when profiling, brackets it with events on `st`.
 struct LaunchScope {

@@ -114,6 +114,33 @@ class Engine:
             S, _np_ptr(sym), _np_ptr(n_sym), _np_ptr(aabb)), 'set_meshes')
         self.n_labels, self.s_max = L, S
 
+    # -- device rasteriser ------------------------------------------------------------------
+    def set_render_meshes(self, vertices, colors, faces, face_offsets):
+        """Triangle meshes of all labels in one table: vertices / colors [Nv,3] (colours in [0,1]), faces [Nf,3]
+        indexing the vertex table, face_offsets [L+1] (label l owns faces face_offsets[l]:face_offsets[l+1])."""
+        v = np.ascontiguousarray(vertices, dtype=np.float32)
+        c = np.ascontiguousarray(colors, dtype=np.float32)
+        f = np.ascontiguousarray(faces, dtype=np.int32)
+        off = np.ascontiguousarray(face_offsets, dtype=np.int32)
+        assert v.ndim == 2 and v.shape[1] == 3 and c.shape == v.shape and f.ndim == 2 and f.shape[1] == 3
+        _lib.check(self._L.cosyb200_set_render_meshes(self._h, len(off) - 1, v.shape[0], _np_ptr(v), _np_ptr(c),
+                                                      f.shape[0], _np_ptr(f), _np_ptr(off)), 'set_render_meshes')
+        self.n_render_labels = len(off) - 1
+
+    def render(self, label_ids, TCO, K, uint8=True, out=None):
+        """Views of B hypotheses at poses TCO [B,4,4] through intrinsics K [B,3,3]: uint8 [B,240,320,3] or
+        float32 [B,3,240,320] in [0,1]."""
+        B = TCO.shape[0]
+        self._chk(label_ids, torch.int32, (B,), 'label_ids')
+        self._chk(TCO, torch.float32, (B, 4, 4), 'TCO')
+        self._chk(K, torch.float32, (B, 3, 3), 'K')
+        if out is None:
+            out = (torch.empty((B, 240, 320, 3), dtype=torch.uint8, device=self.device) if uint8
+                   else self._new(B, 3, 240, 320))
+        _lib.check(self._L.cosyb200_render(self._h, B, _ptr(label_ids), _ptr(TCO), _ptr(K), _ptr(out), int(uint8),
+                                           self._stream()), 'render')
+        return out
+
     # -- single-view path ---------------------------------------------------------------------
     def tco_init(self, boxes, K, label_ids, zup=False):
         B = boxes.shape[0]
@@ -188,16 +215,22 @@ class Engine:
             _ptr(K_crop), _ptr(TCO), _ptr(pose9), _ptr(TCO_out), self._stream()), 'refine_iter')
         return pose9, TCO_out
 
-    def refine_n(self, slot, images, im_ids, K, label_ids, renders, TCO, out=None):
+    def refine_n(self, slot, images, im_ids, K, label_ids, renders, TCO, out=None, n_iter=None):
         """n_iter = renders.shape[0] iterations on pre-rendered views; returns a dict of
-        per-iteration tensors (TCO_output, K_crop, boxes_rend, boxes_crop, pose)."""
-        n_iter, B = renders.shape[:2]
+        per-iteration tensors (TCO_output, K_crop, boxes_rend, boxes_crop, pose).
+        renders=None with n_iter given: every iteration rasterises its own views on the device
+        (set_render_meshes first)."""
+        if renders is None:
+            assert n_iter is not None and n_iter >= 1, 'refine_n without views needs n_iter'
+            B = TCO.shape[0]
+        else:
+            n_iter, B = renders.shape[:2]
         n_im, c, H, W = images.shape
         self._chk(images, torch.float32, name='images')
         self._chk(im_ids, torch.int32, (B,), 'im_ids')
         self._chk(K, torch.float32, (B, 3, 3), 'K')
         self._chk(label_ids, torch.int32, (B,), 'label_ids')
-        u8 = self._chk_renders(renders, (n_iter, B))
+        u8 = self._chk_renders(renders, (n_iter, B)) if renders is not None else 1
         self._chk(TCO, torch.float32, (B, 4, 4), 'TCO')
         if out is None:
             out = dict(TCO_output=self._new(n_iter, B, 4, 4), K_crop=self._new(n_iter, B, 3, 3),
@@ -205,7 +238,7 @@ class Engine:
                        pose=self._new(n_iter, B, 9))
         _lib.check(self._L.cosyb200_refine_n(
             self._h, slot, B, n_iter, _ptr(images), n_im, H, W, _ptr(im_ids), _ptr(K), _ptr(label_ids),
-            _ptr(renders), u8, _ptr(TCO), _ptr(out['TCO_output']), _ptr(out['K_crop']), _ptr(out['boxes_rend']),
+            _ptr(renders) if renders is not None else c_void_p(None), u8, _ptr(TCO), _ptr(out['TCO_output']), _ptr(out['K_crop']), _ptr(out['boxes_rend']),
             _ptr(out['boxes_crop']), _ptr(out['pose']), self._stream()), 'refine_n')
         return out
 
@@ -264,21 +297,21 @@ class Engine:
 
     # -- launch accounting --------------------------------------------------------------------
     CATEGORIES = ('geometry', 'roi_crop', 'stem', 'expand_1x1', 'depthwise', 'squeeze_excite',
-                  'project_1x1', 'head_1x1', 'pool_fc_update', 'ransac')
+                  'project_1x1', 'head_1x1', 'pool_fc_update', 'ransac', 'render')
 
     def profile_enable(self, on=True):
         _lib.check(self._L.cosyb200_profile_enable(self._h, int(on)), 'profile_enable')
 
     def profile_read(self, reset=True):
         """{category: (launches, device_ms)} since the last reset (ms only while profiling)."""
-        n = np.zeros(10, dtype=np.int64)
-        ms = np.zeros(10, dtype=np.float64)
+        n = np.zeros(len(self.CATEGORIES), dtype=np.int64)
+        ms = np.zeros(len(self.CATEGORIES), dtype=np.float64)
         _lib.check(self._L.cosyb200_profile_read(self._h, int(reset), _np_ptr(n), _np_ptr(ms)), 'profile_read')
         return {c: (int(n[i]), float(ms[i])) for i, c in enumerate(self.CATEGORIES)}
 
     def profile_read_blocks(self, reset=True):
         """{category: [device_ms per MBConv block (index 31: outside the blocks)]} while profiling."""
-        ms = np.zeros((10, 32), dtype=np.float64)
+        ms = np.zeros((len(self.CATEGORIES), 32), dtype=np.float64)
         _lib.check(self._L.cosyb200_profile_read_blocks(self._h, int(reset), _np_ptr(ms)), 'profile_read_blocks')
         return {c: ms[i].tolist() for i, c in enumerate(self.CATEGORIES)}
 

@@ -7,7 +7,9 @@ libcosyb200.so.  One iteration is two engine calls with the renderer in between:
     pose9, TCO_out = engine.refine_iter(images, im_ids, boxes_crop, renders, ...)  # pose.py:104-108
 
 A renderer that exposes `prerendered(n_iterations, batch_size)` (all views known up front, as in
-the synthetic benchmark) lets the whole loop run in one engine call (`refine_n`).
+the synthetic benchmark) lets the whole loop run in one engine call (`refine_n`); so does the
+engine's own rasteriser (`rendering.CudaRasterizer`, attribute `in_engine`), which draws every
+iteration's views on the device between the crop geometry and the network.
 """
 from types import SimpleNamespace
 
@@ -82,8 +84,10 @@ class PosePredictor:
         stack = None
         if hasattr(self.renderer, 'prerendered'):
             stack = self.renderer.prerendered(n_iterations, bsz)
-        if stack is not None:
-            out = eng.refine_n(self.slot, images, im_ids, K, label_ids, stack, TCO_input)
+        in_engine = stack is None and getattr(self.renderer, 'in_engine', False)
+        if stack is not None or in_engine:
+            # views known up front, or rasterised by the engine itself: the whole loop is one engine call
+            out = eng.refine_n(self.slot, images, im_ids, K, label_ids, stack, TCO_input, n_iter=n_iterations)
             for n in range(n_iterations):
                 outputs[f'iteration={n + 1}'] = {
                     'TCO_input': TCO_input if n == 0 else out['TCO_output'][n - 1],

@@ -84,3 +84,67 @@ class PerCallRenderer:
 
     def render(self, *args, **kwargs):
         return self.views.render(*args, **kwargs)
+
+
+class RenderMeshTable:
+    """Triangle meshes of a label set packed for the engine's rasteriser: one vertex / colour table, one face
+    table with global vertex ids, per-label face ranges.  Label order must match the `BatchedMeshes`
+    the pose models use (its `label_to_id`)."""
+
+    def __init__(self, labels, vertices, faces, colors=None):
+        """labels: list of str; vertices[l] [Nv_l,3] float (metres, object frame); faces[l] [Nf_l,3] int
+        (ids into vertices[l]); colors[l] [Nv_l,3] in [0,1] (default: mid grey)."""
+        import numpy as np
+        assert len(labels) == len(vertices) == len(faces)
+        self.labels = list(labels)
+        self.label_to_id = {l: i for i, l in enumerate(self.labels)}
+        vs, cs, fs, off, base = [], [], [], [0], 0
+        for l in range(len(labels)):
+            v = np.asarray(vertices[l], dtype=np.float32).reshape(-1, 3)
+            f = np.asarray(faces[l], dtype=np.int64).reshape(-1, 3)
+            assert f.size == 0 or (f.min() >= 0 and f.max() < len(v)), f'faces of {labels[l]} index outside its vertices'
+            c = (np.full_like(v, 0.5) if colors is None or colors[l] is None
+                 else np.asarray(colors[l], dtype=np.float32).reshape(-1, 3))
+            assert c.shape == v.shape
+            vs.append(v)
+            cs.append(c)
+            fs.append((f + base).astype(np.int32))
+            base += len(v)
+            off.append(off[-1] + len(f))
+        self.vertices = np.concatenate(vs, axis=0)
+        self.colors = np.concatenate(cs, axis=0)
+        self.faces = np.concatenate(fs, axis=0)
+        self.face_offsets = np.asarray(off, dtype=np.int32)
+
+    def label_ids(self, labels):
+        import numpy as np
+        return np.asarray([self.label_to_id[l] for l in labels], dtype=np.int32)
+
+
+class CudaRasterizer:
+    """Renderer with the reference's call contract (reference: rendering/bullet_batch_renderer.py:46-90:
+    `render(obj_infos, TCO, K, resolution)` -> float [B,3,240,320] in [0,1], background 0) drawn by
+    libcosyb200.so on the hypotheses' own GPU: no worker processes, queue, pickling or pinned copy.
+
+    `in_engine = True` tells `PosePredictor` that the views need not leave the engine at all: all
+    iterations of a batch then run as one `refine_n` call (and one CUDA graph) that rasterises between
+    the crop geometry and the network."""
+    in_engine = True
+
+    def __init__(self, engine, mesh_table, as_uint8=True):
+        self.engine = engine
+        self.table = mesh_table
+        self.as_uint8 = as_uint8
+        engine.set_render_meshes(mesh_table.vertices, mesh_table.colors, mesh_table.faces, mesh_table.face_offsets)
+
+    def render(self, obj_infos, TCO, K, resolution=(240, 320), render_depth=False):
+        assert tuple(resolution) == (240, 320), 'the engine renders 240x320 views'
+        assert not render_depth, 'depth output is not part of the refinement path'
+        dev = self.engine.device
+        label_ids = torch.from_numpy(self.table.label_ids([o['name'] for o in obj_infos])).to(dev)
+        TCO = torch.as_tensor(TCO).detach().to(dev, torch.float32).contiguous()
+        K = torch.as_tensor(K).detach().to(dev, torch.float32).contiguous()
+        bsz = len(TCO)
+        assert TCO.shape == (bsz, 4, 4)
+        assert K.shape == (bsz, 3, 3)
+        return self.engine.render(label_ids, TCO, K, uint8=self.as_uint8)

@@ -278,3 +278,54 @@ def make_net_input(n, seed=21):
     shape = (n, 3, spec.RENDER_H, spec.RENDER_W)
     obs = _smooth_field(gen, shape, coarse=16, dtype=torch.float32)
     return torch.cat((obs, _render_like(gen, shape, dtype=torch.float32)), dim=1).contiguous()
+
+
+def make_icosphere(subdiv=2, radius=0.05):
+    """Unit icosahedron subdivided `subdiv` times (20 * 4^subdiv faces), vertices on a sphere of `radius` metres."""
+    t = (1.0 + 5.0 ** 0.5) / 2.0
+    v = [(-1, t, 0), (1, t, 0), (-1, -t, 0), (1, -t, 0), (0, -1, t), (0, 1, t), (0, -1, -t), (0, 1, -t),
+         (t, 0, -1), (t, 0, 1), (-t, 0, -1), (-t, 0, 1)]
+    f = [(0, 11, 5), (0, 5, 1), (0, 1, 7), (0, 7, 10), (0, 10, 11), (1, 5, 9), (5, 11, 4), (11, 10, 2), (10, 7, 6),
+         (7, 1, 8), (3, 9, 4), (3, 4, 2), (3, 2, 6), (3, 6, 8), (3, 8, 9), (4, 9, 5), (2, 4, 11), (6, 2, 10),
+         (8, 6, 7), (9, 8, 1)]
+    v = [np.asarray(p, dtype=np.float64) / np.linalg.norm(p) for p in v]
+    for _ in range(subdiv):
+        mid, nf = {}, []
+
+        def midpoint(a, b):
+            key = (min(a, b), max(a, b))
+            if key not in mid:
+                m = v[a] + v[b]
+                v.append(m / np.linalg.norm(m))
+                mid[key] = len(v) - 1
+            return mid[key]
+        for a, b, c in f:
+            ab, bc, ca = midpoint(a, b), midpoint(b, c), midpoint(c, a)
+            nf += [(a, ab, ca), (b, bc, ab), (c, ca, bc), (ab, bc, ca)]
+        f = nf
+    return (np.asarray(v) * radius).astype(np.float32), np.asarray(f, dtype=np.int32)
+
+
+def make_render_meshes(n_labels, seed=2, subdiv=2, extent=0.1):
+    """Per label a closed triangle mesh with smooth per-vertex colours: even labels a deformed icosphere
+    (many pixel-sized triangles), odd labels a box of 12 triangles (triangles spanning the view), so both
+    paths of the rasteriser are exercised.  Returns (vertices, faces, colors) lists."""
+    rs = np.random.RandomState(seed)
+    verts, faces, cols = [], [], []
+    for l in range(n_labels):
+        if l % 2 == 0:
+            v, f = make_icosphere(subdiv, radius=0.5 * extent)
+            scale = rs.uniform(0.6, 1.0, size=3).astype(np.float32)
+            bump = 1.0 + 0.15 * np.sin(v @ rs.uniform(-60, 60, size=3).astype(np.float32))
+            v = (v * bump[:, None] * scale).astype(np.float32)
+        else:
+            h = (0.5 * extent * rs.uniform(0.4, 1.0, size=3)).astype(np.float32)
+            v = np.asarray([[sx * h[0], sy * h[1], sz * h[2]] for sx in (-1, 1) for sy in (-1, 1) for sz in (-1, 1)],
+                           dtype=np.float32)
+            f = np.asarray([(0, 1, 3), (0, 3, 2), (4, 6, 7), (4, 7, 5), (0, 4, 5), (0, 5, 1), (2, 3, 7), (2, 7, 6),
+                            (0, 2, 6), (0, 6, 4), (1, 5, 7), (1, 7, 3)], dtype=np.int32)
+        c = 0.5 + 0.5 * np.sin(v / extent * rs.uniform(4, 12, size=3) + rs.uniform(0, 6.28, size=3))
+        verts.append(v)
+        faces.append(f)
+        cols.append(c.astype(np.float32))
+    return verts, faces, cols

@@ -127,10 +127,32 @@ int cosyb200_refine_iter(cosyb200_handle* h, int slot, int B, const float* image
                          const float* K_crop_dev, const float* TCO_in_dev, float* pose9_dev,
                          float* TCO_out_dev, void* stream);
 
+/* ---- device rasteriser ----
+ * Replaces the renderer side input of the loop (reference: models/pose.py:100-102 -> rendering/bullet_batch_renderer.py:46-90:
+ * one pybullet getCameraImage per hypothesis in worker processes, frames back through a multiprocessing queue and a
+ * pinned copy).  Camera as simulator/camera.py:10-34 builds it from K: pinhole, samples at pixel centres (j+0.5, i+0.5),
+ * near plane 0.01 (triangles reaching in front of it are dropped, not clipped), nearest surface wins, background 0,
+ * both faces drawn; colour = perspective-correct interpolation of per-vertex colours, unlit (pybullet's shading is not
+ * reproducible here: DESIGN.md).
+ *   cosyb200_set_render_meshes   host tables: vertices / colors [n_vertices,3] (object frame, metres; colours in [0,1]),
+ *       faces [n_faces,3] int32 ids into the vertex table, face_offsets [n_labels+1]: label l owns faces
+ *       face_offsets[l] .. face_offsets[l+1]-1 (label ids as in cosyb200_set_meshes).
+ *   cosyb200_render   B views at TCO_dev [B,4,4] with intrinsics K_dev [B,3,3] (K_crop of cosyb200_prepare_iter):
+ *       out_u8 = 1 -> uint8 [B,240,320,3] (the layout refine_iter takes with render_u8 = 1),
+ *       out_u8 = 0 -> fp32 [B,3,240,320] = uint8 / 255 as bullet_batch_renderer.py:83 returns it. */
+int cosyb200_set_render_meshes(cosyb200_handle* h, int n_labels, int64_t n_vertices, const float* vertices,
+                               const float* colors, int64_t n_faces, const int32_t* faces,
+                               const int32_t* face_offsets);
+int cosyb200_render(cosyb200_handle* h, int B, const int32_t* label_ids_dev, const float* TCO_dev,
+                    const float* K_dev, void* out_dev, int out_u8, void* stream);
+
 /* PosePredictor.forward with pre-rendered views (reference: models/pose.py:89-132): n_iter
  * iterations without returning to the host.  renders_dev [n_iter,B,3,240,320]; K_dev [B,3,3];
  * outputs are per iteration: TCO_out [n_iter,B,4,4], K_crop [n_iter,B,3,3], boxes_rend and
- * boxes_crop [n_iter,B,4], pose9 [n_iter,B,9]; iteration n reads TCO_out[n-1] (TCO_in_dev for n=0). */
+ * boxes_crop [n_iter,B,4], pose9 [n_iter,B,9]; iteration n reads TCO_out[n-1] (TCO_in_dev for n=0).
+ * renders_dev == NULL: every iteration rasterises its own views on the device from the meshes of
+ * cosyb200_set_render_meshes at the iteration's input poses and K_crop (the reference's loop, pose.py:99-102,
+ * with the renderer inside the engine: nothing returns to the host between iterations). */
 int cosyb200_refine_n(cosyb200_handle* h, int slot, int B, int n_iter, const float* images_dev,
                       int n_images, int img_h, int img_w, const int32_t* im_ids_dev,
                       const float* K_dev, const int32_t* label_ids_dev, const void* renders_dev,
@@ -139,14 +161,14 @@ int cosyb200_refine_n(cosyb200_handle* h, int slot, int B, int n_iter, const flo
 
 /* Engine options (all choose between implementations of the same arithmetic; results agree within the
  * tolerances of tests/test_gpu_*.py):
- *   "gemm_impl": 1 (default) runs the 1x1 convolutions on the tcgen05 tensor cores with the 3xTF32 split,
- *                0 on CUDA cores in plain fp32 (kept as the per-block parity anchor);
+ *   "gemm_impl": 2 (default) runs the 1x1 convolutions on the tcgen05 tensor cores with the 3xFP16 hi/lo split
+ *                (kernels_pw2.cuh), 1 = the 3xTF32 kernel, 0 = CUDA cores in plain fp32 (the per-block parity anchor);
+ *   "xdw":       1 (default) blocks 2-8 run expand 1x1 + depthwise + pooling as one kernel (kernels_xdw.cuh), 0 = separately;
  *   "dw_impl":   1 (default) shared-memory tiled depthwise + split squeeze-excite for the blocks with
  *                output <= 30x40, 0 = rolling-window depthwise + k_se_gate everywhere;
- *   "tc_groups": 0 (default) picks the tensor-core kernel variant per layer, 1 / 2 force one / two
- *                producer warpgroups (process-wide);
- *   "tc_tma":    0 (default) raw A stages of the tensor-core kernel by cp.async, 1 = EXPERIMENTAL TMA-fed stages
- *                (faster, not yet bit-reproducible: DESIGN.md section 8; "tc_dbg" sets its experiment bits). */
+ *   "tc_groups": 0 (default) picks the 3xTF32 kernel variant per layer, 1 / 2 force one / two producer warpgroups;
+ *   "graph":     1 (default) cosyb200_refine_n replays a captured CUDA graph when its arguments repeat, 0 = plain launches;
+ *   "trace_block": debugging, -1 (default) off: the fused kernel of that block stamps its phases (cosyb200_debug_trace). */
 int cosyb200_set_option(cosyb200_handle* h, const char* name, int value);
 
 /* One 1x1 convolution on caller data, for kernel-level tests (reference: the Conv2d 1x1 + folded
@@ -169,13 +191,13 @@ int cosyb200_debug_dump(cosyb200_handle* h, int block, float* expanded, float* d
 /* Launch accounting (no reference counterpart; the reference times with a wall-clock Timer,
  * utils/timer.py:4-36).  Every kernel the engine launches is counted per category:
  *   0 geometry, 1 roi crop, 2 stem, 3 expand 1x1, 4 depthwise, 5 squeeze-excite, 6 project 1x1,
- *   7 head 1x1, 8 pool+fc+update, 9 ransac.
+ *   7 head 1x1, 8 pool+fc+update, 9 ransac, 10 rasteriser.
  * With profiling enabled each launch is also bracketed by CUDA events on its stream and the
  * device time accumulated per category (adds launch overhead: use outside timed regions). */
 int cosyb200_profile_enable(cosyb200_handle* h, int on);
-int cosyb200_profile_read(cosyb200_handle* h, int reset, int64_t* launches10, double* ms10);
+int cosyb200_profile_read(cosyb200_handle* h, int reset, int64_t* launches11, double* ms11);
 /* The same device time split per MBConv block: ms[category * 32 + block], block 31 = stem / head / outside. */
-int cosyb200_profile_read_blocks(cosyb200_handle* h, int reset, double* ms320);
+int cosyb200_profile_read_blocks(cosyb200_handle* h, int reset, double* ms352);
 
 /* ---- multiview candidate matching (reference: multiview/ransac.py:137-199) ---- */
 
