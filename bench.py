@@ -217,7 +217,7 @@ class SingleViewJob:
         return pd.DataFrame(d)
 
 
-def build_predictor(job, device_index):
+def build_predictor(job, device_index, views_mode='prerendered'):
     from helpers import state_dict
     from cosypose_b200.engine import Engine
     from cosypose_b200.integrated.pose_predictor import CoarseRefinePosePredictor
@@ -227,7 +227,15 @@ def build_predictor(job, device_index):
     eng = Engine(device_index, max_batch=BSZ)
     mesh_db = BatchedMeshes.from_tables(job.labels, job.points, job.sym, job.n_sym)
     mesh_db.install(eng)
-    views = PreRenderedViews([job.views_c, job.views_r], BSZ, device=eng.device)
+    if views_mode == 'engine':
+        # the engine's own rasteriser draws every iteration's views: even labels a 20 480-triangle
+        # closed surface, odd labels a 12-triangle box
+        from cosypose_b200 import synthetic as syn
+        from cosypose_b200.rendering import CudaRasterizer, RenderMeshTable
+        v, f, col = syn.make_render_meshes(len(job.labels), subdiv=5)
+        views = CudaRasterizer(eng, RenderMeshTable(job.labels, v, f, col))
+    else:
+        views = PreRenderedViews([job.views_c, job.views_r], BSZ, device=eng.device)
     coarse = PosePredictor(eng, 0, views, mesh_db).load_state_dict(state_dict(0))
     refiner = PosePredictor(eng, 1, views, mesh_db).load_state_dict(state_dict(1))
     return CoarseRefinePosePredictor(coarse, refiner, bsz_objects=BSZ), eng, views, mesh_db
@@ -240,7 +248,8 @@ def run_single_view(args, cfg, rank, local_rank, world):
     c = CONFIGS[cfg]
     dev = torch.device('cuda', local_rank)
     job = SingleViewJob(cfg, rank, world)
-    pred, eng, views, mesh_db = build_predictor(job, local_rank)
+    engine_views = args.views == 'engine'
+    pred, eng, views, mesh_db = build_predictor(job, local_rank, args.views)
     if world > 1:
         eng.nccl_init()
     infos = job.infos()
@@ -269,7 +278,8 @@ def run_single_view(args, cfg, rank, local_rank, world):
         return final.poses
 
     def step_resident():
-        views.reset()
+        if not engine_views:
+            views.reset()
         final, _ = pred.get_predictions(d_images, d_K, detections=det, n_coarse_iterations=c['n_coarse'],
                                         n_refiner_iterations=c['n_refine'], shard=world > 1)
         return finish(final)
@@ -278,8 +288,9 @@ def run_single_view(args, cfg, rank, local_rank, world):
     # loop would.  Views travel as uint8 NHWC, the reference renderer's native output (bullet_batch_renderer.py:70-83).
     h_images = job.images_local.pin_memory()
     h_K, h_boxes = job.K.pin_memory(), job.boxes.pin_memory()
-    h_views = [(v[:, s0:s0 + BSZ] * 255).round().to(torch.uint8).permute(0, 1, 3, 4, 2).contiguous().pin_memory()
-               for v in (job.views_c, job.views_r) for s0 in range(0, job.n_local, BSZ)]   # one stack per chunk, call order
+    h_views = [] if engine_views else [
+        (v[:, s0:s0 + BSZ] * 255).round().to(torch.uint8).permute(0, 1, 3, 4, 2).contiguous().pin_memory()
+        for v in (job.views_c, job.views_r) for s0 in range(0, job.n_local, BSZ)]   # one stack per chunk, call order
     h_out = torch.empty((job.n, 4, 4), dtype=torch.float32).pin_memory()
     h2d = h_images.numel() * 4 + h_K.numel() * 4 + h_boxes.numel() * 4 + sum(v.numel() for v in h_views)
     d2h = h_out.numel() * 4
@@ -291,7 +302,7 @@ def run_single_view(args, cfg, rank, local_rank, world):
             self.images = torch.zeros_like(d_images)
             self.K, self.boxes = torch.empty_like(d_K), torch.empty_like(d_boxes)
             self.views = [torch.empty(v.shape, dtype=torch.uint8, device=dev) for v in h_views]
-            self.rv = PreRenderedViews.from_chunks(self.views, BSZ)
+            self.rv = views if engine_views else PreRenderedViews.from_chunks(self.views, BSZ)
             self.det = tc.PandasTensorCollection(infos=infos, bboxes=self.boxes)
             self.ready, self.done = torch.cuda.Event(), torch.cuda.Event()
             self.done.record()
@@ -318,7 +329,8 @@ def run_single_view(args, cfg, rank, local_rank, world):
         s = sets[i % 2]
         cur = torch.cuda.current_stream()
         cur.wait_event(s.ready)
-        s.rv.reset()
+        if not engine_views:
+            s.rv.reset()
         pred.coarse_model.renderer = s.rv
         pred.refiner_model.renderer = s.rv
         final, _ = pred.get_predictions(s.images, s.K, detections=s.det, n_coarse_iterations=c['n_coarse'],
@@ -387,7 +399,9 @@ def run_single_view(args, cfg, rank, local_rank, world):
                           % (job.n_local * (c['n_coarse'] + c['n_refine']) * 0.92, fwd_per_step_rank * 0.0244),
                     'collective': ('one ncclAllGather of %d floats per hypothesis and step (cosyb200_allgather_candidates)'
                                    % ((c['n_coarse'] + c['n_refine']) * 49)) if world > 1 else 'none',
-                    'rank_data': 'rank-distinct frames, detections and views (shards of one global table)'},
+                    'rank_data': 'rank-distinct frames, detections and views (shards of one global table)',
+                    'views': ('rasterised by the engine inside every iteration (20 480-triangle surfaces and 12-triangle boxes); '
+                              'the CPU baseline consumes pre-generated views') if engine_views else 'pre-rendered (uint8 NHWC on the e2e leg)'},
             clocks=clocks,
             e2e={'value': hyps / (ms_e2e * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': int(h2d),
                  'd2h_bytes_per_step': int(d2h), 'ms_per_step': ms_e2e / args.steps},
@@ -670,6 +684,9 @@ def main():
     ap.add_argument('--config', type=int, default=1, choices=[1, 2, 3, 4])
     ap.add_argument('--cpu-sample', type=int, default=16, help='hypotheses in the CPU baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--views', default='prerendered', choices=['prerendered', 'engine'],
+                    help="'prerendered' (BASELINE.json: renders pre-generated, the default) or 'engine': every iteration's views "
+                         'drawn by the engine rasteriser inside the loop')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
 

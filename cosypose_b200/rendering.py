@@ -148,3 +148,6 @@ class CudaRasterizer:
         assert TCO.shape == (bsz, 4, 4)
         assert K.shape == (bsz, 3, 3)
         return self.engine.render(label_ids, TCO, K, uint8=self.as_uint8)
+
+    def reset(self):
+        pass
