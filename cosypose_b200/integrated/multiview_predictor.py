@@ -28,11 +28,10 @@ class MultiviewScenePredictor:
         """TCO = inv(TWC) @ TWO for every (object, view), object-major (reference: :20-41)."""
         n_o, n_v = len(objects), len(cameras)
         dev = self.engine.device
-        io = torch.arange(n_o, dtype=torch.int32, device=dev).repeat_interleave(n_v)
-        iv = torch.arange(n_v, dtype=torch.int32, device=dev).repeat(n_o)
+        o, v = np.repeat(np.arange(n_o, dtype=np.int32), n_v), np.tile(np.arange(n_v, dtype=np.int32), n_o)
+        d_ov = torch.from_numpy(np.stack((o, v))).to(dev)
         poses = self.engine.compose_inv(cameras.TWC.to(dev, torch.float32).contiguous(),
-                                        objects.TWO.to(dev, torch.float32).contiguous(), iv, io)
-        o, v = io.cpu().numpy(), iv.cpu().numpy()
+                                        objects.TWO.to(dev, torch.float32).contiguous(), d_ov[1], d_ov[0])
         oi, ci = objects.infos, cameras.infos
         infos = pd.DataFrame(dict(
             scene_id=ci['scene_id'].values[v], view_id=ci['view_id'].values[v],
@@ -45,10 +44,12 @@ class MultiviewScenePredictor:
                             ransac_n_iter=2000, ransac_dist_threshold=0.02, ba_n_iter=100):
         predictions = dict()
         cand_inputs = candidates
-        assert len(np.unique(candidates.infos['scene_id'])) == 1
-        scene_id = np.unique(candidates.infos['scene_id']).item()
-        group_id = np.unique(candidates.infos['group_id']).item()
-        candidates = candidates[np.where(candidates.infos['score'] >= score_th)[0]]
+        scene_ids = np.unique(candidates.infos['scene_id'].to_numpy())
+        assert len(scene_ids) == 1
+        scene_id = scene_ids.item()
+        group_id = np.unique(candidates.infos['group_id'].to_numpy()).item()
+        keep = np.flatnonzero(candidates.infos['score'].to_numpy() >= score_th)
+        candidates = candidates[keep]
         predictions['cand_inputs'] = candidates
 
         matching = multiview_candidate_matching(
@@ -59,20 +60,28 @@ class MultiviewScenePredictor:
         predictions['cand_matched'] = candidates
 
         group_infos = make_view_groups(pairs_TC1C2)
-        candidates = candidates.merge_df(group_infos, on='view_id').to(self.engine.device)
+        view_to_group = dict(zip(group_infos['view_id'].to_numpy().tolist(), group_infos['view_group'].to_numpy().tolist()))
+        cand_views = candidates.infos['view_id'].to_numpy().tolist()
+        if all(v in view_to_group for v in cand_views):     # the left merge of the reference (:72), without pandas
+            infos = candidates.infos.assign(view_group=np.asarray([view_to_group[v] for v in cand_views],
+                                                                  dtype=group_infos['view_group'].to_numpy().dtype))
+            candidates = tc.PandasTensorCollection(infos=infos, **dict(candidates.tensors)).to(self.engine.device)
+        else:
+            candidates = candidates.merge_df(group_infos, on='view_id').to(self.engine.device)
 
         pred_objects, pred_cameras, pred_reproj, pred_reproj_init = [], [], [], []
-        for view_group, candidate_ids in candidates.infos.groupby('view_group').groups.items():
-            problem = MultiviewRefinement(candidates=candidates[np.asarray(candidate_ids)], cameras=cameras,
+        cand_groups = candidates.infos['view_group'].to_numpy()
+        for view_group in np.unique(cand_groups).tolist():
+            candidate_ids = np.flatnonzero(cand_groups == view_group)
+            problem = MultiviewRefinement(candidates=candidates[candidate_ids], cameras=cameras,
                                           pairs_TC1C2=pairs_TC1C2, mesh_db=self.mesh_db_ba)
+            # every scene collection the problem emits carries its group / scene columns (:88-93)
+            tags = dict(view_group=view_group, group_id=group_id, scene_id=scene_id)
+            problem.obj_infos = problem.obj_infos.assign(**tags)
+            problem.cam_infos = problem.cam_infos.assign(**tags)
             ba = problem.solve(n_iterations=ba_n_iter, optimize_cameras=not use_known_camera_poses)
-            for key_o, key_c, sink in (('objects', 'cameras', pred_reproj),
-                                       ('objects_init', 'cameras_init', pred_reproj_init)):
-                for x in (ba[key_o], ba[key_c]):
-                    x.infos['view_group'] = view_group
-                    x.infos['group_id'] = group_id
-                    x.infos['scene_id'] = scene_id
-                sink.append(self.reproject_scene(ba[key_o], ba[key_c]))
+            pred_reproj.append(self.reproject_scene(ba['objects'], ba['cameras']))
+            pred_reproj_init.append(self.reproject_scene(ba['objects_init'], ba['cameras_init']))
             pred_objects.append(ba['objects'])
             pred_cameras.append(ba['cameras'])
 

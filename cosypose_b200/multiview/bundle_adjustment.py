@@ -75,45 +75,97 @@ def invert_T(T):
     return out
 
 
+class LazyHistory(dict):
+    """The optimisation history of `MultiviewRefinement.solve`; the per-iteration scene collections are materialised
+    when 'objects' or 'cameras' is first read."""
+
+    def __init__(self, history, problem):
+        super().__init__(history)
+        self._problem = problem
+
+    def _materialise(self):
+        if not dict.__contains__(self, 'objects'):
+            pairs = self._problem._scene_infos_many(list(zip(dict.__getitem__(self, 'TWO_9d'),
+                                                             dict.__getitem__(self, 'TCW_9d'))))
+            dict.__setitem__(self, 'objects', [o for o, _ in pairs])
+            dict.__setitem__(self, 'cameras', [c for _, c in pairs])
+
+    def __getitem__(self, key):
+        if key in ('objects', 'cameras'):
+            self._materialise()
+        return dict.__getitem__(self, key)
+
+    def __contains__(self, key):
+        return key in ('objects', 'cameras') or dict.__contains__(self, key)
+
+    def get(self, key, default=None):
+        return self[key] if key in self else default
+
+    def __reduce__(self):       # pickles as the plain, fully materialised dict
+        self._materialise()
+        return (dict, (dict(dict.items(self)),))
+
+    def keys(self):
+        self._materialise()
+        return dict.keys(self)
+
+    def items(self):
+        self._materialise()
+        return dict.items(self)
+
+
 class MultiviewRefinement:
     def __init__(self, candidates, cameras, pairs_TC1C2, mesh_db):
         self.mesh_db = mesh_db
         self.engine = eng = mesh_db.engine
         self.device = eng.device
 
-        view_ids = np.unique(candidates.infos['view_id'])
-        keep = np.isin(pairs_TC1C2.infos['view1'], view_ids) & np.isin(pairs_TC1C2.infos['view2'], view_ids)
-        pairs_TC1C2 = pairs_TC1C2[np.where(keep)[0]]
-        cameras = cameras[np.where(np.isin(cameras.infos['view_id'], view_ids))[0]]
+        cand_views = candidates.infos['view_id'].to_numpy()
+        cand_objs = candidates.infos['obj_id'].to_numpy()
+        view_ids = np.unique(cand_views)
+        pv1, pv2 = pairs_TC1C2.infos['view1'].to_numpy(), pairs_TC1C2.infos['view2'].to_numpy()
+        keep = np.flatnonzero(np.isin(pv1, view_ids) & np.isin(pv2, view_ids))
+        cam_keep = np.flatnonzero(np.isin(cameras.infos['view_id'].to_numpy(), view_ids))
+        if len(cam_keep) != len(cameras):
+            cameras = cameras[cam_keep]
 
         self.cam_infos = cameras.infos
-        self.view_to_id = {v: n for n, v in enumerate(self.cam_infos['view_id'])}
+        self.view_to_id = {v: n for n, v in enumerate(self.cam_infos['view_id'].to_numpy().tolist())}
         self.K = cameras.K.to(self.device, torch.float32).contiguous()
         self.n_views = len(self.cam_infos)
 
         self.obj_infos = make_obj_infos(candidates)
-        self.obj_to_id = {o: n for n, o in enumerate(self.obj_infos['obj_id'])}
+        self.obj_to_id = {o: n for n, o in enumerate(self.obj_infos['obj_id'].to_numpy().tolist())}
         self.n_objects = len(self.obj_infos)
         self.points = mesh_db.points.to(self.device, torch.float32).contiguous()   # [L, P, 3]
         self.n_points = self.points.shape[1]
 
         self.cand = candidates
         self.cand_TCO = candidates.poses.to(self.device, torch.float32).contiguous()
-        self.cand_view_ids = np.array([self.view_to_id[v] for v in candidates.infos['view_id']], dtype=np.int32)
-        self.cand_obj_ids = np.array([self.obj_to_id[o] for o in candidates.infos['obj_id']], dtype=np.int32)
+        self.cand_view_ids = np.array([self.view_to_id[v] for v in cand_views.tolist()], dtype=np.int32)
+        self.cand_obj_ids = np.array([self.obj_to_id[o] for o in cand_objs.tolist()], dtype=np.int32)
         self.n_candidates = len(self.cand_TCO)
-        self._d_view = torch.from_numpy(self.cand_view_ids).to(self.device)
-        self._d_obj = torch.from_numpy(self.cand_obj_ids).to(self.device)
-        self._d_label = torch.from_numpy(mesh_db.label_ids(candidates.infos['label'].values)).to(self.device)
+        # one upload for the three per-candidate index columns
+        idx = np.stack((self.cand_view_ids, self.cand_obj_ids,
+                        mesh_db.label_ids(candidates.infos['label'].to_numpy()))).astype(np.int32)
+        d_idx = torch.from_numpy(idx).to(self.device)
+        self._d_view, self._d_obj, self._d_label = d_idx[0], d_idx[1], d_idx[2]
 
         self.visibility = np.zeros((self.n_objects, self.n_views), dtype=bool)
         self.visibility[self.cand_obj_ids, self.cand_view_ids] = True
 
-        TC1C2 = pairs_TC1C2.TC1C2.detach().cpu().numpy() if len(pairs_TC1C2) else np.zeros((0, 4, 4), np.float32)
-        self.v2v1_TC2C1 = {(self.view_to_id[v2], self.view_to_id[v1]): invert_T(T)
-                           for v1, v2, T in zip(pairs_TC1C2.infos['view1'], pairs_TC1C2.infos['view2'], TC1C2)}
-        cand_np = self.cand_TCO.cpu().numpy()
-        self.ov_TCO = {(int(o), int(v)): T for o, v, T in zip(self.cand_obj_ids, self.cand_view_ids, cand_np)}
+        # one download for the relative camera poses and the candidate poses
+        n_pairs = len(keep)
+        if n_pairs:
+            sel = torch.as_tensor(keep, device=pairs_TC1C2.TC1C2.device)
+            both = torch.cat((pairs_TC1C2.TC1C2[sel].to(self.device, torch.float32), self.cand_TCO), dim=0).cpu().numpy()
+        else:
+            both = self.cand_TCO.cpu().numpy()
+        TC1C2, cand_np = both[:n_pairs], both[n_pairs:]
+        TC2C1 = invert_T(TC1C2) if n_pairs else TC1C2
+        self.v2v1_TC2C1 = {(self.view_to_id[v2], self.view_to_id[v1]): T
+                           for v1, v2, T in zip(pv1[keep].tolist(), pv2[keep].tolist(), TC2C1)}
+        self.ov_TCO = {(o, v): T for o, v, T in zip(self.cand_obj_ids.tolist(), self.cand_view_ids.tolist(), cand_np)}
 
     # -- initialisation (reference: :112-157) --------------------------------------------------
     def sample_initial_TWO_TWC(self, seed):
@@ -214,19 +266,29 @@ class MultiviewRefinement:
 
     # -- outputs ---------------------------------------------------------------------------------
     def make_scene_infos(self, TWO_9d, TCW_9d):
-        TWO = transform_from_pose9d(TWO_9d.cpu().numpy())
-        TWC = invert_T(transform_from_pose9d(TCW_9d.cpu().numpy()))
-        objects = tc.PandasTensorCollection(infos=self.obj_infos, TWO=torch.from_numpy(TWO).to(self.device))
-        cameras = tc.PandasTensorCollection(infos=self.cam_infos, TWC=torch.from_numpy(TWC).to(self.device), K=self.K)
-        return objects, cameras
+        return self._scene_infos_many([(TWO_9d, TCW_9d)])[0]
+
+    def _scene_infos_many(self, states):
+        """(objects, cameras) collections for a list of (TWO_9d, TCW_9d) states: one download of all parameter
+        vectors, the 9-D -> 4x4 conversion on the host (as the reference, :280-293), one upload."""
+        n_o, n_v = self.n_objects, self.n_views
+        flat = torch.cat([x.reshape(-1, 9) for st in states for x in st], dim=0).cpu().numpy()
+        T = transform_from_pose9d(flat)
+        per = n_o + n_v
+        for k in range(len(states)):
+            T[k * per + n_o:(k + 1) * per] = invert_T(T[k * per + n_o:(k + 1) * per])
+        d_T = torch.from_numpy(T).to(self.device)
+        out = []
+        for k in range(len(states)):
+            objects = tc.PandasTensorCollection(infos=self.obj_infos, TWO=d_T[k * per:k * per + n_o])
+            cameras = tc.PandasTensorCollection(infos=self.cam_infos, TWC=d_T[k * per + n_o:(k + 1) * per], K=self.K)
+            out.append((objects, cameras))
+        return out
 
     def convert_history(self, history):
-        history['objects'], history['cameras'] = [], []
-        for TWO_9d, TCW_9d in zip(history['TWO_9d'], history['TCW_9d']):
-            objects, cameras = self.make_scene_infos(TWO_9d, TCW_9d)
-            history['objects'].append(objects)
-            history['cameras'].append(cameras)
-        return history
+        """`history['objects']` / `history['cameras']` (one collection per LM iteration, :295-303) are only read by
+        the reference's visualisation: they are built on first access."""
+        return LazyHistory(history, self)
 
     def solve(self, sample_n_init=1, **lm_kwargs):
         timer_init, timer_opt, timer_misc = Timer(), Timer(), Timer()
@@ -237,8 +299,8 @@ class MultiviewRefinement:
         TWO_9d_opt, TCW_9d_opt, history = self.optimize_lm(TWO_9d_init, TCW_9d_init, **lm_kwargs)
         timer_opt.pause()
         timer_misc.start()
-        objects, cameras = self.make_scene_infos(TWO_9d_opt, TCW_9d_opt)
-        objects_init, cameras_init = self.make_scene_infos(TWO_9d_init, TCW_9d_init)
+        (objects, cameras), (objects_init, cameras_init) = self._scene_infos_many(
+            [(TWO_9d_opt, TCW_9d_opt), (TWO_9d_init, TCW_9d_init)])
         history = self.convert_history(history)
         timer_misc.pause()
         return dict(objects_init=objects_init, cameras_init=cameras_init, objects=objects, cameras=cameras,

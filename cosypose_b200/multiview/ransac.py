@@ -31,13 +31,11 @@ def scene_level_matching(candidates, inliers):
     _, ids = connected_components(graph, directed=True, connection='strong')
     sizes = np.bincount(ids, minlength=1)[ids] if n_cand else np.zeros(0, dtype=int)
 
-    cand_infos = candidates.infos.copy()
-    cand_infos['component_id'] = ids
-    cand_infos = cand_infos[sizes >= 2].reset_index(drop=True)
-    # renumber the kept components 0..n-1 in ascending component id
-    _, dense = np.unique(cand_infos['component_id'].values, return_inverse=True)
-    cand_infos['component_id'] = dense
-    cand_infos = cand_infos.rename(columns={'component_id': 'obj_id'})
+    # kept components renumbered 0..n-1 in ascending component id; `obj_id` is appended as the last column
+    keep = np.flatnonzero(sizes >= 2)
+    _, dense = np.unique(ids[keep], return_inverse=True)
+    cand_infos = candidates.infos.iloc[keep].reset_index(drop=True)
+    cand_infos['obj_id'] = dense
     poses = candidates.poses[torch.as_tensor(cand_infos['cand_id'].values.astype(np.int64),
                                              device=candidates.poses.device)]
     return tc.PandasTensorCollection(infos=cand_infos, poses=poses)
@@ -45,11 +43,14 @@ def scene_level_matching(candidates, inliers):
 
 def make_obj_infos(matched_candidates):
     """One row per object: summed score, number of candidates (reference: ransac.py:119-125)."""
-    scene_infos = matched_candidates.infos.loc[:, ['obj_id', 'score', 'label']].copy()
-    gb = scene_infos.groupby('obj_id')
-    scene_infos['n_cand'] = gb['score'].transform('size').astype(int)
-    scene_infos['score'] = gb['score'].transform('sum')
-    return scene_infos.groupby('obj_id').first().reset_index(drop=False)
+    infos = matched_candidates.infos
+    obj_ids, first, inv = np.unique(infos['obj_id'].to_numpy(), return_index=True, return_inverse=True)
+    score = infos['score'].to_numpy()
+    # per object: sum of the scores in row order, number of rows, label of the first row
+    total = np.zeros(len(obj_ids), dtype=np.result_type(score.dtype, np.float32))
+    np.add.at(total, inv, score)
+    return pd.DataFrame(dict(obj_id=obj_ids, score=total, label=infos['label'].to_numpy()[first],
+                             n_cand=np.bincount(inv, minlength=len(obj_ids)).astype(int)))
 
 
 def get_best_viewpair_pose_est(TC1C2, seeds, inliers):

@@ -146,6 +146,8 @@ def concatenate(datas):
     if not datas:
         return PandasTensorCollection(infos=pd.DataFrame())
     assert all(type(d) is type(datas[0]) for d in datas)
+    if len(datas) == 1:     # a fresh collection over the same rows (its constructor re-indexes a copy of infos)
+        return PandasTensorCollection(infos=datas[0].infos, **dict(datas[0].tensors))
     infos = pd.concat([d.infos for d in datas], axis=0, sort=False).reset_index(drop=True)
     tensors = {k: torch.cat([getattr(d, k) for d in datas], dim=0) for k in datas[0].tensors}
     return PandasTensorCollection(infos=infos, **tensors)
