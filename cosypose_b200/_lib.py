@@ -40,7 +40,7 @@ _SIGS = {
     'cosyb200_refine_n': ([_P, c_int, c_int, c_int, _P, c_int, c_int, c_int, _P, _P, _P, _P, c_int, _P,
                            _P, _P, _P, _P, _P, _P], c_int),
     'cosyb200_set_render_meshes': ([_P, c_int, c_int64, _P, _P, c_int64, _P, _P], c_int),
-    'cosyb200_render': ([_P, c_int, _P, _P, _P, _P, c_int, _P], c_int),
+    'cosyb200_render': ([_P, c_int, _P, _P, _P, _P, c_int, _P, _P], c_int),
     'cosyb200_set_option': ([_P, c_char_p, c_int], c_int),
     'cosyb200_nccl_unique_id': ([_P], c_int),
     'cosyb200_nccl_comm_init': ([_P, c_int, c_int, _P], c_int),

@@ -906,7 +906,7 @@ int cosyb200_set_render_meshes(cosyb200_handle* h, int n_labels, int64_t n_verti
 }
 
 static int launch_render(cosyb200_handle* h, int B, const int32_t* label_ids, const float* TCO, const float* K,
-                         void* out, int out_u8, cudaStream_t st) {
+                         void* out, int out_u8, float* depth, cudaStream_t st) {
   if (h->r_labels == 0) { set_error("render: render meshes not set (cosyb200_set_render_meshes)"); return COSYB200_ESTATE; }
   const size_t npix = (size_t)B * RENDER_H * RENDER_W;
   static_assert(RENDER_H % raster::TILE == 0 && RENDER_W % raster::TILE == 0, "resolve tiles must cover the view");
@@ -924,21 +924,21 @@ static int launch_render(cosyb200_handle* h, int B, const int32_t* label_ids, co
     const dim3 grid(RENDER_W / raster::TILE, RENDER_H / raster::TILE, B);
     if (out_u8)
       raster::k_raster_resolve<true><<<grid, 256, 0, st>>>(h->r_verts, h->r_colors, h->r_faces, TCO, K, h->r_zbuf,
-                                                           h->r_big_cnt, h->r_big_list, h->r_max_faces, out);
+                                                           h->r_big_cnt, h->r_big_list, h->r_max_faces, out, depth);
     else
       raster::k_raster_resolve<false><<<grid, 256, 0, st>>>(h->r_verts, h->r_colors, h->r_faces, TCO, K, h->r_zbuf,
-                                                            h->r_big_cnt, h->r_big_list, h->r_max_faces, out);
+                                                            h->r_big_cnt, h->r_big_list, h->r_max_faces, out, depth);
   }
   CB_LAUNCH_CHECK();
   return COSYB200_OK;
 }
 
 int cosyb200_render(cosyb200_handle* h, int B, const int32_t* label_ids, const float* TCO, const float* K, void* out,
-                    int out_u8, void* stream) {
+                    int out_u8, float* depth, void* stream) {
   if (int rc = check_batch(h, B, "render")) return rc;
   CB_CHECK_ARG(label_ids && TCO && K && out, "render: null argument");
   DeviceGuard guard(h->device);
-  return launch_render(h, B, label_ids, TCO, K, out, out_u8, (cudaStream_t)stream);
+  return launch_render(h, B, label_ids, TCO, K, out, out_u8, depth, (cudaStream_t)stream);
 }
 
 int cosyb200_refine_iter(cosyb200_handle* h, int slot, int B, const float* images, int n_images,
@@ -974,7 +974,7 @@ int cosyb200_refine_n(cosyb200_handle* h, int slot, int B, int n_iter, const flo
       int views_u8 = render_u8;
       if (!renders) {   // no views handed in: rasterise the hypotheses at their current poses (pose.py:100-102)
         DeviceGuard guard(h->device);
-        rc = launch_render(h, B, io.label_ids, tin, io.K_crop + (size_t)n * B * 9, h->r_frames, 1, (cudaStream_t)st);
+        rc = launch_render(h, B, io.label_ids, tin, io.K_crop + (size_t)n * B * 9, h->r_frames, 1, nullptr, (cudaStream_t)st);
         if (rc) return rc;
         views = h->r_frames;
         views_u8 = 1;

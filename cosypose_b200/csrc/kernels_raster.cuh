@@ -192,7 +192,8 @@ __global__ void __launch_bounds__(256)
 k_raster_resolve(const float* __restrict__ verts, const float* __restrict__ colors, const int32_t* __restrict__ faces,
                  const float* __restrict__ TCO, const float* __restrict__ Kc,
                  const unsigned long long* __restrict__ zbuf, const int* __restrict__ big_cnt,
-                 const int* __restrict__ big_list, int max_faces, void* __restrict__ out) {
+                 const int* __restrict__ big_list, int max_faces, void* __restrict__ out,
+                 float* __restrict__ depth /*[B][240][320] camera z, 0 = background; may be null*/) {
   __shared__ TriS s_tri[256];
   __shared__ float s_T[12], s_K[6];
   const int b = blockIdx.z, tid = threadIdx.x;
@@ -243,6 +244,7 @@ k_raster_resolve(const float* __restrict__ verts, const float* __restrict__ colo
       }
     }
   }
+  if (depth) depth[idx] = key != EMPTY_KEY ? __uint_as_float((unsigned int)(key >> 32)) : 0.f;
   unsigned char q[3];
 #pragma unroll
   for (int c = 0; c < 3; ++c) q[c] = (unsigned char)__float2int_rn(__fmul_rn(rgb[c], 255.f));

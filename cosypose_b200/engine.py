@@ -127,9 +127,9 @@ class Engine:
                                                       f.shape[0], _np_ptr(f), _np_ptr(off)), 'set_render_meshes')
         self.n_render_labels = len(off) - 1
 
-    def render(self, label_ids, TCO, K, uint8=True, out=None):
+    def render(self, label_ids, TCO, K, uint8=True, out=None, depth=False):
         """Views of B hypotheses at poses TCO [B,4,4] through intrinsics K [B,3,3]: uint8 [B,240,320,3] or
-        float32 [B,3,240,320] in [0,1]."""
+        float32 [B,3,240,320] in [0,1]; depth=True also returns camera z [B,240,320] (0 = background)."""
         B = TCO.shape[0]
         self._chk(label_ids, torch.int32, (B,), 'label_ids')
         self._chk(TCO, torch.float32, (B, 4, 4), 'TCO')
@@ -137,9 +137,10 @@ class Engine:
         if out is None:
             out = (torch.empty((B, 240, 320, 3), dtype=torch.uint8, device=self.device) if uint8
                    else self._new(B, 3, 240, 320))
+        d = self._new(B, 240, 320) if depth else None
         _lib.check(self._L.cosyb200_render(self._h, B, _ptr(label_ids), _ptr(TCO), _ptr(K), _ptr(out), int(uint8),
-                                           self._stream()), 'render')
-        return out
+                                           _ptr(d), self._stream()), 'render')
+        return (out, d) if depth else out
 
     # -- single-view path ---------------------------------------------------------------------
     def tco_init(self, boxes, K, label_ids, zup=False):

@@ -116,6 +116,15 @@ class RenderMeshTable:
         self.faces = np.concatenate(fs, axis=0)
         self.face_offsets = np.asarray(off, dtype=np.int32)
 
+    @classmethod
+    def from_ply(cls, labels, paths, scale=0.001):
+        """One PLY per label (BOP `models/obj_%06d.ply`: millimetres, per-vertex colours); `scale` converts to the
+        metres of the poses (0.001 as the reference loads its BOP URDFs, cosypose/datasets/urdf_dataset.py:31)."""
+        from .lib3d.ply import read_ply
+        meshes = [read_ply(p) for p in paths]
+        return cls(labels, [m['vertices'] * scale for m in meshes], [m['faces'] for m in meshes],
+                   [m['colors'] for m in meshes])
+
     def label_ids(self, labels):
         import numpy as np
         return np.asarray([self.label_to_id[l] for l in labels], dtype=np.int32)
@@ -139,7 +148,6 @@ class CudaRasterizer:
 
     def render(self, obj_infos, TCO, K, resolution=(240, 320), render_depth=False):
         assert tuple(resolution) == (240, 320), 'the engine renders 240x320 views'
-        assert not render_depth, 'depth output is not part of the refinement path'
         dev = self.engine.device
         label_ids = torch.from_numpy(self.table.label_ids([o['name'] for o in obj_infos])).to(dev)
         TCO = torch.as_tensor(TCO).detach().to(dev, torch.float32).contiguous()
@@ -147,7 +155,7 @@ class CudaRasterizer:
         bsz = len(TCO)
         assert TCO.shape == (bsz, 4, 4)
         assert K.shape == (bsz, 3, 3)
-        return self.engine.render(label_ids, TCO, K, uint8=self.as_uint8)
+        return self.engine.render(label_ids, TCO, K, uint8=self.as_uint8, depth=render_depth)
 
     def reset(self):
         pass

@@ -139,12 +139,14 @@ int cosyb200_refine_iter(cosyb200_handle* h, int slot, int B, const float* image
  *       face_offsets[l] .. face_offsets[l+1]-1 (label ids as in cosyb200_set_meshes).
  *   cosyb200_render   B views at TCO_dev [B,4,4] with intrinsics K_dev [B,3,3] (K_crop of cosyb200_prepare_iter):
  *       out_u8 = 1 -> uint8 [B,240,320,3] (the layout refine_iter takes with render_u8 = 1),
- *       out_u8 = 0 -> fp32 [B,3,240,320] = uint8 / 255 as bullet_batch_renderer.py:83 returns it. */
+ *       out_u8 = 0 -> fp32 [B,3,240,320] = uint8 / 255 as bullet_batch_renderer.py:83 returns it;
+ *       depth_dev (may be NULL) [B,240,320]: camera-frame z of the visible surface in metres, 0 on the background
+ *       (render_depth=True of the reference, bullet_scene_renderer.py:51-56). */
 int cosyb200_set_render_meshes(cosyb200_handle* h, int n_labels, int64_t n_vertices, const float* vertices,
                                const float* colors, int64_t n_faces, const int32_t* faces,
                                const int32_t* face_offsets);
 int cosyb200_render(cosyb200_handle* h, int B, const int32_t* label_ids_dev, const float* TCO_dev,
-                    const float* K_dev, void* out_dev, int out_u8, void* stream);
+                    const float* K_dev, void* out_dev, int out_u8, float* depth_dev, void* stream);
 
 /* PosePredictor.forward with pre-rendered views (reference: models/pose.py:89-132): n_iter
  * iterations without returning to the host.  renders_dev [n_iter,B,3,240,320]; K_dev [B,3,3];

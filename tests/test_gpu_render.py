@@ -50,10 +50,12 @@ def test_frames_bit_exact_vs_oracle(subdiv, zscale):
     T[7, 1, 1] = np.nan        # invalid pose: black frame (bullet_batch_renderer.py:27-38)
     K[8, 0, 0] = K[8, 1, 1] = 4000.0   # zoomed in: triangles spanning the whole view
     K[9, 0, 0] = K[9, 1, 1] = 5000.0
-    ref, _, ids = ro.render(tab.vertices, tab.colors, tab.faces, tab.face_offsets, labels, T, K)
-    out = eng.render(torch.from_numpy(labels).to(dev), torch.from_numpy(T).to(dev), torch.from_numpy(K).to(dev))
+    ref, zref, ids = ro.render(tab.vertices, tab.colors, tab.faces, tab.face_offsets, labels, T, K)
+    out, depth = eng.render(torch.from_numpy(labels).to(dev), torch.from_numpy(T).to(dev), torch.from_numpy(K).to(dev),
+                            depth=True)
     torch.cuda.synchronize()
     got = out.cpu().numpy()
+    assert np.array_equal(depth.cpu().numpy(), np.where(ids >= 0, zref, np.float32(0)))
     assert got.shape == (B, 240, 320, 3) and got.dtype == np.uint8
     assert np.array_equal(got, ref), f'{(got != ref).any(axis=-1).sum()} pixels differ'
     covered = (ids >= 0).reshape(B, -1).mean(axis=1)

@@ -71,3 +71,45 @@ def test_near_plane_and_invalid_poses_give_black_frames():
     T[1, 0, 0] = np.nan
     out, _, ids = ro.render(tab.vertices, tab.colors, tab.faces, tab.face_offsets, [0, 1], T, K)
     assert not out.any() and (ids < 0).all()
+
+
+def _write_ply(path, v, f, c, fmt):
+    import struct
+    head = ['ply', f'format {fmt} 1.0', 'comment made by the test', f'element vertex {len(v)}',
+            'property float x', 'property float y', 'property float z', 'property float nx', 'property float ny',
+            'property float nz', 'property uchar red', 'property uchar green', 'property uchar blue',
+            f'element face {len(f)}', 'property list uchar int vertex_indices', 'end_header']
+    c8 = np.rint(c * 255).astype(np.uint8)
+    with open(path, 'wb') as fh:
+        fh.write(('\n'.join(head) + '\n').encode())
+        if fmt == 'ascii':
+            for p, col in zip(v, c8):
+                fh.write(('%r %r %r 0 0 1 %d %d %d\n' % (float(p[0]), float(p[1]), float(p[2]), *col)).encode())
+            for tri in f:
+                fh.write(('3 %d %d %d\n' % tuple(tri)).encode())
+        else:
+            e = '<' if fmt == 'binary_little_endian' else '>'
+            for p, col in zip(v, c8):
+                fh.write(struct.pack(e + '6f3B', p[0], p[1], p[2], 0, 0, 1, *col))
+            for tri in f:
+                fh.write(struct.pack(e + 'B3i', 3, *tri))
+
+
+def test_ply_reader_round_trip(tmp_path):
+    from cosypose_b200.lib3d.ply import read_ply
+    v, f, c = synthetic.make_render_meshes(2)
+    for fmt in ('ascii', 'binary_little_endian', 'binary_big_endian'):
+        p = tmp_path / f'{fmt}.ply'
+        _write_ply(p, v[0] * 1000, f[0], c[0], fmt)
+        m = read_ply(p)
+        assert np.array_equal(m['faces'], f[0]) and m['faces'].dtype == np.int32
+        assert np.allclose(m['vertices'], v[0] * 1000, rtol=1e-6)
+        assert np.abs(m['colors'] - c[0]).max() <= 0.5 / 255 + 1e-6
+    # quads are fan-triangulated; a file without colours gives colors=None
+    q = tmp_path / 'quad.ply'
+    q.write_text('ply\nformat ascii 1.0\nelement vertex 4\nproperty float x\nproperty float y\nproperty float z\n'
+                 'element face 1\nproperty list uchar uint vertex_index\nend_header\n0 0 0\n1 0 0\n1 1 0\n0 1 0\n4 0 1 2 3\n')
+    m = read_ply(q)
+    assert m['colors'] is None and m['faces'].tolist() == [[0, 1, 2], [0, 2, 3]]
+    tab = RenderMeshTable.from_ply(['a', 'b'], [tmp_path / 'ascii.ply', tmp_path / 'binary_little_endian.ply'])
+    assert np.allclose(tab.vertices[:len(v[0])], v[0], atol=1e-7) and tab.face_offsets.tolist() == [0, len(f[0]), 2 * len(f[0])]
