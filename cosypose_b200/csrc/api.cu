@@ -226,11 +226,23 @@ static int launch_pw2(cosyb200_handle* h, bool gate, bool swish, bool resid, con
   const pw2::Plan p = pw2::make_plan(M, N, K, h->n_sms);
   if (p.bn == 0) { set_error("launch_pw2: no plan for M=%d N=%d K=%d", M, N, K); return COSYB200_EINVAL; }
   const int gate_smem = rows_per_img >= 64 ? 1 : 0;
-#define PW2_LAUNCH_S(G, S, R, SM)                                                                                  \
-  pw2::k_pw2<G, S, R, SM><<<p.grid, pw2::THREADS, p.smem_bytes, st>>>(                                             \
+  if (!h->pw_ws) {     // partial-sum slots + flags of the k-stage work split, one per CTA
+    void* p0 = nullptr;
+    if (int rc = dev_alloc(&p0, (size_t)h->n_sms * pw2::WS_SLOT_BYTES + (size_t)h->n_sms * 4)) return rc;
+    h->pw_ws = (float*)p0;
+    h->pw_flags = (int*)((char*)p0 + (size_t)h->n_sms * pw2::WS_SLOT_BYTES);
+    CB_CUDA(cudaMemset(h->pw_flags, 0, (size_t)h->n_sms * 4));
+  }
+  if (p.grid > h->n_sms) { set_error("launch_pw2: grid %d exceeds the SM count", p.grid); return COSYB200_EINVAL; }
+#define PW2_LAUNCH_S(G, S, R, SM, SK)                                                                              \
+  pw2::k_pw2<G, S, R, SM, SK><<<p.grid, pw2::THREADS, p.smem_bytes, st>>>(                                         \
       A, (const __half*)Wp2, bias, g, r, C, M, N, K, rows_per_img, p.bn, p.n_tiles, p.nb, p.resident,             \
-      pw2::n_alloc_for(N), inv_wscale, gate_smem)
-#define PW2_LAUNCH(G, S, R) do { if (p.small) PW2_LAUNCH_S(G, S, R, true); else PW2_LAUNCH_S(G, S, R, false); } while (0)
+      pw2::n_alloc_for(N), inv_wscale, gate_smem, h->pw_ws, h->pw_flags)
+#define PW2_LAUNCH(G, S, R)                                                                                        \
+  do {                                                                                                             \
+    if (p.small) { if (p.split_k) PW2_LAUNCH_S(G, S, R, true, true); else PW2_LAUNCH_S(G, S, R, true, false); }    \
+    else { if (p.split_k) PW2_LAUNCH_S(G, S, R, false, true); else PW2_LAUNCH_S(G, S, R, false, false); }          \
+  } while (0)
   if (!gate && swish && !resid) PW2_LAUNCH(false, true, false);
   else if (gate && !swish && !resid) PW2_LAUNCH(true, false, false);
   else if (gate && !swish && resid) PW2_LAUNCH(true, false, true);
@@ -265,8 +277,10 @@ static int opt_in_gemm_kernels() {
   int rc = 0;
   rc |= opt_in_smem(tc::k_pw_gemm_tc<64, G, S, R, 1>, 112 * 1024);
   rc |= opt_in_smem(tc::k_pw_gemm_tc<64, G, S, R, 2>, 202 * 1024);
-  rc |= opt_in_smem(pw2::k_pw2<G, S, R, false>, 224 * 1024);
-  rc |= opt_in_smem(pw2::k_pw2<G, S, R, true>, 224 * 1024);
+  rc |= opt_in_smem(pw2::k_pw2<G, S, R, false, false>, 224 * 1024);
+  rc |= opt_in_smem(pw2::k_pw2<G, S, R, true, false>, 224 * 1024);
+  rc |= opt_in_smem(pw2::k_pw2<G, S, R, false, true>, 224 * 1024);
+  rc |= opt_in_smem(pw2::k_pw2<G, S, R, true, true>, 224 * 1024);
   return rc;
 }
 
@@ -594,7 +608,8 @@ int cosyb200_destroy(cosyb200_handle* h) {
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   void* ptrs[] = {h->act[0], h->act[1], h->buf_e, h->buf_d, h->pool_partial, h->gate, h->crops, h->pose9,
                   h->pts_sampled, h->sym, h->n_sym, h->aabb, h->io_buf, h->ba_ws, h->lm_ws, h->vote_ws,
-                  h->r_verts, h->r_colors, h->r_faces, h->r_face_off, h->r_zbuf, h->r_frames, h->r_big_cnt, h->r_big_list};
+                  h->r_verts, h->r_colors, h->r_faces, h->r_face_off, h->r_zbuf, h->r_frames, h->r_big_cnt, h->r_big_list,
+                  h->pw_ws};
   for (void* p : ptrs) if (p) cudaFree(p);
   delete h;
   return COSYB200_OK;

@@ -117,6 +117,7 @@ struct cosyb200_handle {
   float* gate = nullptr;               // [B][cexp_max]
   float* crops = nullptr;              // [B][3][240][320]
   float* pose9 = nullptr;              // [B][9] scratch
+  float* pw_ws = nullptr; int* pw_flags = nullptr;   // k_pw2: partial sums + flags of tiles split over two CTAs
   // device rasteriser (cosyb200_set_render_meshes / cosyb200_render; kernels_raster.cuh)
   float* r_verts = nullptr;            // [n_vertices][3] object frame
   float* r_colors = nullptr;           // [n_vertices][3] in [0, 1]

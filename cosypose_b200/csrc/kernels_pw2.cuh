@@ -16,8 +16,16 @@
 // truncations instead of 22 with the tf32 kernel's schedule per 64 k) and the partial sums are added in registers
 // with round-to-nearest.
 //
-// Structure (one CTA per SM, 16 warps = 4 warpgroups with setmaxnreg budgets, persistent over the m-tiles of one
-// n-tile).  Two shapes of the same kernel:
+// Work split ("stream-K" along m-tile x k-stage): the CTAs of one n-tile column share its m_tiles * nk k-stage units in
+// equal contiguous ranges, so a CTA works through the tail of one m-tile, whole m-tiles, and the head of another.  With
+// whole tiles only, 150 m-tiles on 148 SMs (every 15x20 layer at 64 hypotheses) took two rounds, and 35 m-tiles x 2
+// n-tiles (the 7x10 layers) left half the SMs idle; now those layers split each tile's K over two CTAs.  A tile is shared
+// by at most two CTAs: the one holding its first k-stage owns it, the other writes its fp32 partial sums to a per-CTA
+// workspace slot (L2) and raises a flag; the owner adds them in a fixed order (own + partner), so results are run-to-run
+// identical and no atomics touch data.  Every CTA produces its partial FIRST, so an owner never waits on a CTA that
+// waits on it; all CTAs are co-resident (grid <= SM count, one CTA per SM).
+//
+// Structure (one CTA per SM, 16 warps = 4 warpgroups with setmaxnreg budgets).  Two shapes of the same kernel:
 //                       BIG (bn <= 192)                          SMALL (bn <= 96: HBM / latency bound layers)
 //   converters          warps 0-3                                warps 0-7: two groups on alternate k-stages
 //   drain + epilogue    warps 4-11: 2 per TMEM lane quadrant,    warps 8-11: one per quadrant, all columns
@@ -139,6 +147,15 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, float* v) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void st_global_v4_if(float* p, const float4& v, bool ok) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %5, 0;\n"
+      "@p st.global.v4.f32 [%0], {%1, %2, %3, %4};\n"
+      "}\n" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"((int)ok)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // fp16 pair: `lo_k` (even k) in bits 0-15, `hi_k` (odd k) in bits 16-31
 __device__ __forceinline__ uint32_t pack_f16x2(float even_k, float odd_k) {
@@ -152,9 +169,12 @@ __device__ __forceinline__ void split11(float x, float& hi, float& lo) {
   lo = x - hi;
 }
 
-// Work split of a launch: CTA c owns n-tile c % n_tiles and m-tiles c / n_tiles + i * (gridDim.x / n_tiles).
+// Work split of a launch: CTA c owns n-tile c % n_tiles; with j = c / n_tiles and P = gridDim.x / n_tiles it takes
+//   split_k = 0: the whole m-tiles j, j + P, j + 2P, ... (concurrent CTAs stream neighbouring rows: the HBM-bound layers);
+//   split_k = 1: the k-stage units [j U / P, (j + 1) U / P) of the column, U = m_tiles * nk, unit u = (m-tile u / nk,
+//                k-stage u % nk): long-K layers whose m-tile count does not fill the SMs evenly.
 struct Plan {
-  int bn, small, n_tiles, nk, nb, resident, smem_bytes, grid;
+  int bn, small, n_tiles, nk, nb, resident, smem_bytes, grid, split_k;
 };
 
 __device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
@@ -163,11 +183,14 @@ __device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
 
 // Wpk: [nk][2 (hi|lo)][4 chunks][n_alloc rows][8 halfs] fp16, rows >= N zero; n_alloc >= n_tiles * bn.
 // gate_smem: the gate rows travel through the raw ring (needs rows_per_img >= 64); otherwise they are read from global.
-template <bool GATE, bool SWISH, bool RESID, bool SMALL>
+template <bool GATE, bool SWISH, bool RESID, bool SMALL, bool SPLITK>
 __global__ void __launch_bounds__(THREADS, 1)
 k_pw2(const float* __restrict__ A, const __half* __restrict__ Wpk, const float* __restrict__ bias,
       const float* __restrict__ gate, const float* __restrict__ resid, float* __restrict__ C, int M, int N, int K,
-      int rows_per_img, int bn, int n_tiles, int nb, int resident, int n_alloc, float inv_wscale, int gate_smem) {
+      int rows_per_img, int bn, int n_tiles, int nb, int resident, int n_alloc, float inv_wscale, int gate_smem,
+      float* __restrict__ ws /*[grid][BN_MAX / 4][128] float4 partial sums*/, int* __restrict__ flags /*[grid]*/) {
+  // SPLITK: contiguous k-stage ranges (tiles may be shared by two CTAs); else whole m-tiles part, part + n_parts, ...
+  static_assert(DS == 1, "the k-stage work split drains every k-stage");
   constexpr int NCG = SMALL ? 2 : 1;                      // converter groups
   constexpr int DRAIN_WARP0 = 4 * NCG;
   constexpr int N_DRAIN = n_drain_warps(SMALL);
@@ -186,10 +209,12 @@ k_pw2(const float* __restrict__ A, const __half* __restrict__ Wpk, const float* 
   const int warp = __shfl_sync(0xffffffffu, tid / 32, 0);
   const int nk = (K + BK - 1) / BK;
   const int m_tiles = (M + BM - 1) / BM;
-  const int n_tile = blockIdx.x % n_tiles, m_first = blockIdx.x / n_tiles, m_step = gridDim.x / n_tiles;
-  const int my_tiles = m_first < m_tiles ? (m_tiles - 1 - m_first) / m_step + 1 : 0;
-  const int n_items = my_tiles * nk;
-  const int ngrp = (nk + DS - 1) / DS;                    // drain groups per tile
+  const int n_tile = blockIdx.x % n_tiles, part = blockIdx.x / n_tiles, n_parts = gridDim.x / n_tiles;
+  // k-stage units of this CTA: item i = (m-tile tile0 + ((s0 + i) / nk) * tstep, k-stage (s0 + i) % nk), i < n_items
+  const long long n_units = (long long)m_tiles * nk;
+  const int u0 = SPLITK ? (int)(part * n_units / n_parts) : 0, u1 = SPLITK ? (int)((part + 1) * n_units / n_parts) : 0;
+  const int tile0 = SPLITK ? u0 / nk : part, s0 = SPLITK ? u0 % nk : 0, tstep = SPLITK ? 1 : n_parts;
+  const int n_items = SPLITK ? u1 - u0 : (part < m_tiles ? (m_tiles - 1 - part) / n_parts + 1 : 0) * nk;
   auto rawFull = [&](int s) { return smem_u32(&bars[s]); };
   auto rawEmpty = [&](int s) { return smem_u32(&bars[MAX_RAW + s]); };
   auto fullA = [&](int s) { return smem_u32(&bars[2 * MAX_RAW + s]); };
@@ -235,7 +260,7 @@ k_pw2(const float* __restrict__ A, const __half* __restrict__ Wpk, const float* 
     const int grp = warp / 4, q = warp % 4;
     const int row = q * 32 + lane;                          // tile row == TMEM lane
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
-    int s = grp % nk, m0 = (m_first + (grp / nk) * m_step) * BM;   // (k-stage, first row) of this group's item
+    int s = (s0 + grp) % nk, m0 = (tile0 + ((s0 + grp) / nk) * tstep) * BM;   // (k-stage, first row) of this group's item
     int img_local = 0, prev_m0 = -1;
     const float* gptr = gate;
     for (int i = grp; i < n_items; i += NCG) {
@@ -297,7 +322,7 @@ k_pw2(const float* __restrict__ A, const __half* __restrict__ Wpk, const float* 
       mbar_arrive(fullA(slot));
       if (tr) trace(64 + 4 * i + 3);
       s += NCG;
-      while (s >= nk) { s -= nk; m0 += m_step * BM; }
+      while (s >= nk) { s -= nk; m0 += tstep * BM; }
     }
   } else if (warp >= MMA_WARP) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
@@ -305,7 +330,7 @@ k_pw2(const float* __restrict__ A, const __half* __restrict__ Wpk, const float* 
       // ---------------------------------------------------------------- MMA issuer
       const uint32_t idesc = make_idesc_f16(bn);
       const uint32_t lbo = (uint32_t)bn * 16u;
-      int s = 0, gg = 0;
+      int s = s0, gg = 0;
       for (int g = 0; g < n_items; ++g) {
         const int slot = g % N_ASLOTS;
         const int b = gg % NACC;
@@ -352,7 +377,7 @@ k_pw2(const float* __restrict__ A, const __half* __restrict__ Wpk, const float* 
         const int n0 = n_tile * bn;
         const int n_loads = resident ? min(nk, n_items) : n_items;
         const uint32_t chunk_bytes = (uint32_t)bn * 16u;
-        int s = 0;
+        int s = s0;
         for (int g = 0; g < n_loads; ++g) {
           const int bslot = resident ? s : g % nb;
           if (!resident && g >= nb) mbar_wait(emptyB(bslot), ((g / nb) - 1) & 1);
@@ -375,14 +400,14 @@ k_pw2(const float* __restrict__ A, const __half* __restrict__ Wpk, const float* 
       const int r0 = lt >> 3, kc = lt & 7;                  // chunk kc of rows r0, r0 + 8, ..., r0 + 120
       const uint32_t dst_thr = raw_base + r0 * RAW_ROW_BYTES + kc * 16;
       const int n_imgs = (M + rows_per_img - 1) / rows_per_img;
-      int s = 0, m0 = m_first * BM, img0 = 0;
+      int s = s0, m0 = tile0 * BM, img0 = 0;
       uint32_t roff[16];
       uint32_t vmask = 0;
       const char* tile_base = reinterpret_cast<const char*>(A);
       for (int i = 0; i < n_items; ++i) {
         const int rslot = i % RAW_DEPTH;
         const int k0 = s * BK;
-        if (s == 0) {
+        if (s == 0 || (SPLITK && i == 0)) {
           if (GATE) img0 = m0 / rows_per_img;
           tile_base = reinterpret_cast<const char*>(A + (size_t)m0 * K + kc * 4);
           vmask = 0;
@@ -410,7 +435,7 @@ k_pw2(const float* __restrict__ A, const __half* __restrict__ Wpk, const float* 
                      ok ? (const void*)(gate + (size_t)img * K + k0 + kc * 4) : (const void*)A, ok);
         }
         cp_async_arrive_noinc(rawFull(rslot));
-        if (++s == nk) { s = 0; m0 += m_step * BM; }
+        if (++s == nk) { s = 0; m0 += tstep * BM; }
       }
       cp_async_wait<0>();
     }
@@ -426,11 +451,14 @@ k_pw2(const float* __restrict__ A, const __half* __restrict__ Wpk, const float* 
     const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
     float* stg = stg_base + dw * STG_WARP_FLOATS;
     float acc[HALF_MAX];
-    const int n_groups = my_tiles * ngrp;
-    int gi = 0, t = 0;
-    for (int gg = 0; gg < n_groups; ++gg) {
+    const int n_groups = n_items;                  // DS == 1: one drain per k-stage unit
+    int seg_s0 = 0;                                // first k-stage of the current tile segment
+    int s_cur = s0, t = tile0;                     // (k-stage, m-tile) of the current unit
+    for (int gg = 0; gg < n_groups; ++gg, ++s_cur) {
       const int b = gg % NACC;
-      if (gi == 0) {
+      if (s_cur == nk) { s_cur = 0; t += tstep; }
+      if (s_cur == 0 || (SPLITK && gg == 0)) {
+        seg_s0 = s_cur;
 #pragma unroll
         for (int i = 0; i < HALF_MAX; ++i) acc[i] = 0.f;
       }
@@ -457,10 +485,44 @@ k_pw2(const float* __restrict__ A, const __half* __restrict__ Wpk, const float* 
       tc_fence_before();
       mbar_arrive(acc_empty(b));
       if (trd) trace(192 + 4 * gg + 2);
-      if (gi == ngrp - 1) {
+      const bool seg_last = s_cur == nk - 1 || (SPLITK && gg == n_groups - 1);
+      if (SPLITK && seg_last && seg_s0 > 0) {
+        // Tail of a tile another CTA owns (the one before this in the column): hand over the partial sums.
+        float4* slot = reinterpret_cast<float4*>(ws) + (size_t)(blockIdx.x - n_tiles) * (BN_MAX / 4) * BM + q * 32 + lane;
+#pragma unroll
+        for (int c = 0; c < HALF_MAX; c += 4)
+          if (c < width) slot[((c_base + c) >> 2) * BM] = make_float4(acc[c], acc[c + 1], acc[c + 2], acc[c + 3]);
+        __threadfence();
+        asm volatile("bar.sync 1, %0;" ::"r"(N_DRAIN * 32) : "memory");
+        if (tid == DRAIN_WARP0 * 32) {
+          int* f = flags + (blockIdx.x - n_tiles);
+          asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(f), "r"(1) : "memory");
+        }
+      } else if (seg_last) {
+        if (SPLITK && s_cur != nk - 1) {
+          // Head of a tile whose tail runs on the next CTA of the column: wait for its partial sums, add them.
+          if (tid == DRAIN_WARP0 * 32) {
+            int* f = flags + blockIdx.x;
+            int v;
+            do {
+              asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+            } while (v == 0);
+          }
+          asm volatile("bar.sync 1, %0;" ::"r"(N_DRAIN * 32) : "memory");
+          const float4* slot = reinterpret_cast<const float4*>(ws) + (size_t)blockIdx.x * (BN_MAX / 4) * BM + q * 32 + lane;
+#pragma unroll
+          for (int c = 0; c < HALF_MAX; c += 4) {
+            if (c < width) {
+              const float4 pv = __ldcg(slot + ((c_base + c) >> 2) * BM);
+              acc[c] += pv.x; acc[c + 1] += pv.y; acc[c + 2] += pv.z; acc[c + 3] += pv.w;
+            }
+          }
+          asm volatile("bar.sync 1, %0;" ::"r"(N_DRAIN * 32) : "memory");
+          if (tid == DRAIN_WARP0 * 32) flags[blockIdx.x] = 0;      // consumed: ready for the next launch
+        }
         // Epilogue: the warp's 32 x width tile goes through a 32 x 32 staging tile so that global stores are
         // row-contiguous 128-byte segments; the residual rows are requested before the activation math.
-        const int m_base = (m_first + t * m_step) * BM + q * 32;
+        const int m_base = t * BM + q * 32;
         const int n_base = n_tile * bn + c_base;
         const int c4 = lane & 7, r_lane = lane >> 3;
 #pragma unroll
@@ -498,21 +560,15 @@ k_pw2(const float* __restrict__ A, const __half* __restrict__ Wpk, const float* 
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
                 const int r = r_lane + 4 * j, m = m_base + r;
-                if (m < M) {
-                  float4 ov = *reinterpret_cast<const float4*>(stg + r * STG_PITCH + c4 * 4);
-                  if (RESID) { ov.x += rr[j].x; ov.y += rr[j].y; ov.z += rr[j].z; ov.w += rr[j].w; }
-                  *reinterpret_cast<float4*>(C + (size_t)m * N + n) = ov;
-                }
+                float4 ov = *reinterpret_cast<const float4*>(stg + r * STG_PITCH + c4 * 4);
+                if (RESID) { ov.x += rr[j].x; ov.y += rr[j].y; ov.z += rr[j].z; ov.w += rr[j].w; }
+                st_global_v4_if(C + (size_t)m * N + n, ov, m < M);     // predicated, not branched: 24 of these per tile
               }
             }
             __syncwarp();
           }
         }
         if (trd) trace(192 + 4 * gg + 3);
-        gi = 0;
-        ++t;
-      } else {
-        ++gi;
       }
     }
   }
@@ -525,6 +581,7 @@ k_pw2(const float* __restrict__ A, const __half* __restrict__ Wpk, const float* 
 }
 
 // ---- host side: tile plan and weight packing -------------------------------------------------------
+constexpr size_t WS_SLOT_BYTES = (size_t)(BN_MAX / 4) * BM * 16;   // partial sums of one CTA (kernel argument `ws`)
 constexpr int N_ALLOC_PAD = BN_MAX;   // zero rows after the last real row so any tile's bulk copies stay in bounds
 
 inline int n_alloc_for(int N) { return (N + 15) / 16 * 16 + N_ALLOC_PAD; }
@@ -552,17 +609,33 @@ inline Plan make_plan(int M, int N, int K, int n_sms) {
     p.resident = nk <= p.nb ? 1 : 0;
     if (p.resident) p.nb = nk;
     p.smem_bytes = fixed + p.nb * slot;
-    const int m_par = std::min(m_tiles, std::max(1, n_sms / p.n_tiles));
+    // CTAs per n-tile column.  Whole m-tiles per CTA unless K is long (>= 16 k-stages: a tile's mainloop dwarfs the
+    // fix-up and the extra epilogue of a shared tile) and splitting shortens the busiest CTA by >= 10 %: then either all
+    // the SMs the column can have (equal k-stage ranges, a tile shared by at most two CTAs) or, when the m-tiles do not
+    // even fill half of them (the 7x10 layers: 35 m-tiles), two CTAs per m-tile.
+    const int max_par = std::max(1, n_sms / p.n_tiles);
+    int m_par = std::min(m_tiles, max_par);
+    double units = std::ceil((double)m_tiles / m_par) * nk;           // k-stage units of the busiest CTA
+    double tiles_touched = std::ceil((double)m_tiles / m_par);
+    p.split_k = 0;
+    if (nk >= 16) {
+      int sp = 0;
+      if (m_tiles >= max_par) sp = max_par;
+      else if (2 * m_tiles <= max_par) sp = 2 * m_tiles;
+      if (sp) {
+        const double u2 = std::ceil((double)m_tiles * nk / sp);
+        if (u2 <= 0.9 * units) { p.split_k = 1; m_par = sp; units = u2; tiles_touched = std::ceil(u2 / nk) + 1.0; }
+      }
+    }
     p.grid = m_par * p.n_tiles;
-    const int tiles_per_cta = (m_tiles + m_par - 1) / m_par;
     // cycles per k-stage: tensor pipe (6 MMAs of bn/2 cycles), shared-memory traffic at 128 B/clk (MMA reads of B,
     // raw A in + out, weight ring writes), converter issue
     const double mma = 3.0 * bn;
-    const double smem = (3.0 * 2 * bn * 32 + 2.0 * BM * BK * 4 + (p.resident && tiles_per_cta > 1 ? 0.0 : (double)slot)) / 128.0;
+    const double smem = (3.0 * 2 * bn * 32 + 2.0 * BM * BK * 4 + (p.resident && units > nk ? 0.0 : (double)slot)) / 128.0;
     const double conv = p.small ? 350.0 : 700.0;
     const double stage = std::max(std::max(mma, smem), conv);
     const double epi = 40.0 * bn / 2 / 16 + 600.0;
-    const double cost = tiles_per_cta * (nk * stage + epi) + 3000.0;
+    const double cost = units * stage + tiles_touched * epi + 3000.0;
     if (cost < best_cost) { best_cost = cost; best = p; }
   }
   return best;

