@@ -56,6 +56,9 @@ using namespace tc;   // PTX wrappers (mbarrier, bulk copy, tcgen05 alloc/commit
 constexpr int BM = 128;
 constexpr int BK = 32;                 // fp32 elements of A per k-stage
 constexpr int KSTEPS = BK / 16;        // kind::f16 MMAs are K = 16
+#ifndef PW2_SPLIT_MIN_NK
+#define PW2_SPLIT_MIN_NK 16
+#endif
 #ifndef PW2_DS
 #define PW2_DS 1
 #endif
@@ -618,7 +621,7 @@ inline Plan make_plan(int M, int N, int K, int n_sms) {
     double units = std::ceil((double)m_tiles / m_par) * nk;           // k-stage units of the busiest CTA
     double tiles_touched = std::ceil((double)m_tiles / m_par);
     p.split_k = 0;
-    if (nk >= 16) {
+    if (nk >= PW2_SPLIT_MIN_NK) {
       int sp = 0;
       if (m_tiles >= max_par) sp = max_par;
       else if (2 * m_tiles <= max_par) sp = 2 * m_tiles;
