@@ -223,7 +223,7 @@ static int launch_gemm_tc(cosyb200_handle* h, bool gate, bool swish, bool resid,
 static int launch_pw2(cosyb200_handle* h, bool gate, bool swish, bool resid, const float* A, const void* Wp2,
                       float inv_wscale, const float* bias, const float* g, const float* r, float* C, int M, int N,
                       int K, int rows_per_img, cudaStream_t st) {
-  const pw2::Plan p = pw2::make_plan(M, N, K, h->n_sms);
+  const pw2::Plan p = pw2::make_plan(M, N, K, h->n_sms, h->pw2_nt);
   if (p.bn == 0) { set_error("launch_pw2: no plan for M=%d N=%d K=%d", M, N, K); return COSYB200_EINVAL; }
   const int gate_smem = rows_per_img >= 64 ? 1 : 0;
   if (!h->pw_ws) {     // partial-sum slots + flags of the k-stage work split, one per CTA
@@ -1110,6 +1110,12 @@ int cosyb200_set_option(cosyb200_handle* h, const char* name, int value) {
   }
   if (strcmp(name, "trace_block") == 0) {
     h->trace_block = value;
+    return COSYB200_OK;
+  }
+  if (strcmp(name, "pw2_nt") == 0) {   // tuning aid: force the number of n-tile columns of k_pw2 (0 = cost model)
+    CB_CHECK_ARG(value >= 0 && value <= 64, "set_option: pw2_nt must be in [0, 64]");
+    h->pw2_nt = value;
+    clear_graphs(h);
     return COSYB200_OK;
   }
   if (strcmp(name, "dw_impl") == 0) {

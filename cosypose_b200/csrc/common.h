@@ -165,6 +165,7 @@ struct cosyb200_handle {
   // debugging aid (cosyb200_debug_dump): copies of block `dump_block`'s internal tensors
   int dump_block = -1;
   float* dump_e = nullptr; float* dump_d = nullptr; float* dump_gate = nullptr;
+  int pw2_nt = 0;      // tuning aid: forced n-tile column count of k_pw2 (0 = cost model)
   int gemm_impl = 2;   // 1x1 convolutions: 0 = CUDA-core fp32 kernel, 1 = tcgen05 3xTF32 kernel, 2 = tcgen05 3xFP16 kernel (kernels_pw2.cuh)
   std::vector<cudaEvent_t> ev_pool;   // pairs: [2*i] start, [2*i+1] stop
   std::vector<int> ev_cat;            // category of each recorded pair

@@ -589,7 +589,7 @@ constexpr int N_ALLOC_PAD = BN_MAX;   // zero rows after the last real row so an
 
 inline int n_alloc_for(int N) { return (N + 15) / 16 * 16 + N_ALLOC_PAD; }
 
-inline Plan make_plan(int M, int N, int K, int n_sms) {
+inline Plan make_plan(int M, int N, int K, int n_sms, int force_nt = 0) {
   const int smem_budget = 225 * 1024 - 1024;
   const int n16 = (N + 15) / 16;
   const int m_tiles = (M + BM - 1) / BM;
@@ -598,6 +598,7 @@ inline Plan make_plan(int M, int N, int K, int n_sms) {
   double best_cost = 1e300;
   for (int nt = (n16 * 16 + BN_MAX - 1) / BN_MAX; nt <= n16; ++nt) {
     const int bn = (n16 + nt - 1) / nt * 16;
+    if (force_nt > 0 && nt != force_nt && nt < n16) continue;   // tuning aid: take this column count if it is valid
     if (bn < 16) break;
     if (nt > 1 && bn < 32) break;
     Plan p;
