@@ -94,7 +94,7 @@ def kernel_algorithmic_bytes():
 # DRAM traffic of one trunk forward at the benchmark batch, from the committed ncu capture
 # (profiles/r02_ncu_dram_per_forward.csv: dram__bytes_read.sum + dram__bytes_write.sum summed over every kernel of one
 # forward of 64 hypotheses, crop and geometry included).
-NCU_TRUNK_DRAM_BYTES_PER_FORWARD_BATCH = 5.165e9   # = 80.7 MB per hypothesis, 3.3x the algorithmic 24.43 MB (round 1: 148 MB)
+NCU_TRUNK_DRAM_BYTES_PER_FORWARD_BATCH = 5.171e9   # = 80.7 MB per hypothesis, 3.3x the algorithmic 24.43 MB (round 1: 148 MB)
 TRUNK_CATS = ('stem', 'expand_1x1', 'depthwise', 'squeeze_excite', 'project_1x1', 'head_1x1', 'pool_fc_update')
 
 

@@ -9,6 +9,7 @@ timeout 300 $NCU --profile-from-start off --metrics dram__bytes_read.sum,dram__b
   --clock-control none --csv --log-file gpurun_out/r02_ncu_dram_per_forward.csv python tools/prof_forward.py --multiview \
   > gpurun_out/prof1.log 2>&1
 echo "dram csv lines: $(wc -l < gpurun_out/r02_ncu_dram_per_forward.csv)"
+[ "$1" = "--dram-only" ] && exit 0
 timeout 900 $NCU --profile-from-start off --set full --import-source on --clock-control none \
   --kernel-name 'regex:k_xdw|k_pw2|k_stem|k_roi_crop|k_se_gate|k_se_fc2|k_dw_tile|k_dwconv_roll|k_pool_fc|k_ransac|k_ba_|k_lm_solve|k_vote' \
   --launch-count 70 -f -o /tmp/r02_full python tools/prof_forward.py --multiview > gpurun_out/prof2.log 2>&1
