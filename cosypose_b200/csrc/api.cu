@@ -226,13 +226,6 @@ static int launch_pw2(cosyb200_handle* h, bool gate, bool swish, bool resid, con
   const pw2::Plan p = pw2::make_plan(M, N, K, h->n_sms, h->pw2_nt);
   if (p.bn == 0) { set_error("launch_pw2: no plan for M=%d N=%d K=%d", M, N, K); return COSYB200_EINVAL; }
   const int gate_smem = rows_per_img >= 64 ? 1 : 0;
-  if (!h->pw_ws) {     // partial-sum slots + flags of the k-stage work split, one per CTA
-    void* p0 = nullptr;
-    if (int rc = dev_alloc(&p0, (size_t)h->n_sms * pw2::WS_SLOT_BYTES + (size_t)h->n_sms * 4)) return rc;
-    h->pw_ws = (float*)p0;
-    h->pw_flags = (int*)((char*)p0 + (size_t)h->n_sms * pw2::WS_SLOT_BYTES);
-    CB_CUDA(cudaMemset(h->pw_flags, 0, (size_t)h->n_sms * 4));
-  }
   if (p.grid > h->n_sms) { set_error("launch_pw2: grid %d exceeds the SM count", p.grid); return COSYB200_EINVAL; }
 #define PW2_LAUNCH_S(G, S, R, SM, SK)                                                                              \
   pw2::k_pw2<G, S, R, SM, SK><<<p.grid, pw2::THREADS, p.smem_bytes, st>>>(                                         \
@@ -591,6 +584,15 @@ int cosyb200_create(cosyb200_handle** out, int device, int max_batch) {
   rc |= dev_alloc((void**)&h->pool_partial, B * part * 4);
   rc |= dev_alloc((void**)&h->gate, B * cmax * 4);
   rc |= dev_alloc((void**)&h->crops, B * 3 * RENDER_H * RENDER_W * 4);
+  {   // k_pw2: partial-sum slots + flags of the k-stage work split, one per CTA (flags start at 0, owners reset them)
+    void* p0 = nullptr;
+    rc |= dev_alloc(&p0, (size_t)h->n_sms * pw2::WS_SLOT_BYTES + (size_t)h->n_sms * 4);
+    if (p0) {
+      h->pw_ws = (float*)p0;
+      h->pw_flags = (int*)((char*)p0 + (size_t)h->n_sms * pw2::WS_SLOT_BYTES);
+      if (cudaMemset(h->pw_flags, 0, (size_t)h->n_sms * 4) != cudaSuccess) rc |= 1;
+    }
+  }
   rc |= dev_alloc((void**)&h->pose9, B * POSE_DIM * 4);
   if (rc) { cosyb200_destroy(h); return COSYB200_ENOMEM; }
   *out = h;
