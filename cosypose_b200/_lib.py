@@ -29,6 +29,7 @@ _SIGS = {
     'cosyb200_destroy': ([_P], c_int),
     'cosyb200_effnet_block': ([c_int, POINTER(c_int32)], c_int),
     'cosyb200_launch_plan': ([c_int, c_int, POINTER(c_int32)], c_int),
+    'cosyb200_pw2_plan': ([c_int, c_int, c_int, c_int, POINTER(c_int32)], c_int),
     'cosyb200_load_pose_model': ([_P, c_int, c_int, POINTER(c_char_p), POINTER(c_void_p), POINTER(c_int64)], c_int),
     'cosyb200_set_meshes': ([_P, c_int, c_int, _P, c_int, _P, c_int, _P, _P, _P], c_int),
     'cosyb200_tco_init': ([_P, c_int, c_int, _P, _P, _P, _P, _P], c_int),

@@ -521,6 +521,14 @@ int cosyb200_launch_plan(int idx, int batch, int32_t* out) {
   return COSYB200_OK;
 }
 
+int cosyb200_pw2_plan(int M, int N, int K, int n_sms, int32_t* out) {
+  CB_CHECK_ARG(out != nullptr && M >= 1 && N >= 1 && K >= 1 && n_sms >= 1, "pw2_plan: bad arguments");
+  const pw2::Plan p = pw2::make_plan(M, N, K, n_sms);
+  const int32_t v[9] = {p.bn, p.small, p.n_tiles, p.nk, p.nb, p.resident, p.smem_bytes, p.grid, p.split_k};
+  memcpy(out, v, sizeof(v));
+  return p.bn ? COSYB200_OK : COSYB200_EINVAL;
+}
+
 int cosyb200_create(cosyb200_handle** out, int device, int max_batch) {
   CB_CHECK_ARG(out != nullptr, "create: null out");
   CB_CHECK_ARG(max_batch >= 1 && max_batch <= 4096, "create: max_batch %d outside [1, 4096]", max_batch);

@@ -59,6 +59,13 @@ int cosyb200_effnet_block(int idx, int32_t* out11);
  *            memory bytes, producer groups, output tiles;  [20..27] project 1x1: the same. */
 int cosyb200_launch_plan(int idx, int batch, int32_t* out32);
 
+/* Work split of the 3xFP16 1x1-convolution kernel (gemm_impl = 2, the default) for C[M][N] = A[M][K] W^T on a GPU with
+ * n_sms SMs (host code only): out[9] = n tile width, small-tile kernel shape, n tiles, k stages (of 32), weight slots,
+ * weights resident, dynamic shared memory bytes, grid (CTAs), split_k.  split_k = 1: the CTAs of an n-tile column take
+ * equal contiguous ranges of its (m-tile, k-stage) units, so an m-tile may be shared by two consecutive CTAs (fixed-order
+ * partial-sum hand-over); 0: whole m-tiles per CTA.  tests/test_host_logic.py checks the invariants. */
+int cosyb200_pw2_plan(int M, int N, int K, int n_sms, int32_t* out9);
+
 /* Replaces PosePredictor.load_state_dict (reference: models/pose.py:18-36, weights named as in
  * SURVEY.md section 5).  `names[i]` is a state_dict key, `ptrs_host[i]` its fp32 data, `numels[i]`
  * its element count.  BatchNorm (eps 1e-3) is folded into the conv weights here. */

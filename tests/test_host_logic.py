@@ -306,3 +306,68 @@ def test_launch_plans_fit_the_sm():
                 assert gtiles == -(-M // 128) * n_tiles
                 assert ng == (2 if gtiles <= 148 else 1)
     assert L.cosyb200_launch_plan(26, 64, out) == _lib.EINVAL
+
+
+def test_gemm_work_split_invariants():
+    """k_pw2's work split (host code, no GPU): every CTA is resident (grid <= SMs), shared memory fits, and with
+    split_k the unit ranges tile the (m-tile, k-stage) space exactly with every m-tile shared by at most two
+    CONSECUTIVE CTAs of its column, the first of which holds k-stage 0 (the owner) and never precedes its partner's
+    hand-over in the partner's own order of work: the conditions the fixed-order partial-sum exchange relies on."""
+    import ctypes
+    from cosypose_b200 import _lib, effnet_spec as spec
+    L = _lib.lib()
+    out = (ctypes.c_int32 * 9)()
+    shapes = spec.activation_shapes()
+    n_sms = 148
+    seen_split = set()
+    for batch in (1, 4, 63, 64, 65, 256):
+        layers = []
+        for b, (_, hi, wi, _), (_, ho, wo, _) in zip(spec.BLOCKS, shapes[1:-2], shapes[2:-1]):
+            if b.e != 1:
+                layers.append((batch * hi * wi, b.cexp, b.cin))
+            layers.append((batch * ho * wo, b.cout, b.cexp))
+        layers.append((batch * 70, 1536, 384))
+        for M, N, K in layers:
+            assert L.cosyb200_pw2_plan(M, N, K, n_sms, out) == 0
+            bn, small, n_tiles, nk, nb, resident, smem, grid, split_k = list(out)
+            m_tiles = -(-M // 128)
+            assert bn % 16 == 0 and 16 <= bn <= 192 and bn * n_tiles >= N and (small == 1) == (bn <= 96)
+            assert nk * 32 >= K > (nk - 1) * 32
+            assert 1 <= grid <= n_sms and grid % n_tiles == 0          # one CTA per SM, all co-resident
+            assert smem + 2048 <= 227 * 1024
+            P = grid // n_tiles
+            if not split_k:
+                assert P <= m_tiles                                     # whole m-tiles: part, part + P, ...
+                continue
+            seen_split.add((batch, M, N, K))
+            assert nk >= 16
+            U = m_tiles * nk
+            bounds = [c * U // P for c in range(P + 1)]
+            assert bounds[0] == 0 and bounds[-1] == U
+            owners = {}
+            for c in range(P):
+                u0, u1 = bounds[c], bounds[c + 1]
+                assert u1 > u0
+                tiles = sorted({u // nk for u in range(u0, u1)})
+                for t in tiles:
+                    s_lo = max(u0, t * nk) - t * nk
+                    s_hi = min(u1, (t + 1) * nk) - 1 - t * nk
+                    owners.setdefault(t, []).append((c, s_lo, s_hi))
+                    # a segment is a head (starts at stage 0) or a tail (ends at the last stage), never a middle piece
+                    assert s_lo == 0 or s_hi == nk - 1
+                    # a CTA's tail segment can only be the FIRST tile of its range: it is produced before anything else
+                    if s_lo > 0:
+                        assert t == tiles[0]
+            assert sorted(owners) == list(range(m_tiles))
+            for t, segs in owners.items():
+                assert len(segs) <= 2
+                if len(segs) == 2:
+                    (c0, a0, b0), (c1, a1, b1) = segs
+                    assert c1 == c0 + 1 and a0 == 0 and b0 + 1 == a1 and b1 == nk - 1
+                else:
+                    assert segs[0][1:] == (0, nk - 1)
+    # the layers the split exists for, at the benchmark batch
+    assert (64, 19200, 136, 816) in seen_split and (64, 4480, 232, 1392) in seen_split
+    assert L.cosyb200_pw2_plan(19200, 136, 816, n_sms, out) == 0 and out[7] == 148
+    assert L.cosyb200_pw2_plan(4480, 232, 1392, n_sms, out) == 0 and out[7] == 140
+    assert L.cosyb200_pw2_plan(19200, 816, 136, n_sms, out) == 0 and out[8] == 0       # short K: whole tiles
