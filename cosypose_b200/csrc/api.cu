@@ -987,6 +987,10 @@ int cosyb200_refine_n(cosyb200_handle* h, int slot, int B, int n_iter, const flo
   if (int rc = check_batch(h, B, "refine_n")) return rc;
   CB_CHECK_ARG(n_iter >= 1, "refine_n: n_iter %d", n_iter);
   if (!renders && h->r_labels == 0) { set_error("refine_n: no views given and no render meshes set"); return COSYB200_ESTATE; }
+  if (!renders && h->r_labels != h->n_labels) {
+    set_error("refine_n: render meshes cover %d labels, the mesh tables %d (the same label ids index both)", h->r_labels, h->n_labels);
+    return COSYB200_ESTATE;
+  }
   struct Io { const int32_t* im_ids; const float* K; const int32_t* label_ids; const float* TCO_in;
               float *TCO_out, *K_crop, *boxes_rend, *boxes_crop, *pose9; };
   auto run = [&](void* st, const Io& io) -> int {
