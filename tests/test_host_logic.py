@@ -371,3 +371,56 @@ def test_gemm_work_split_invariants():
     assert L.cosyb200_pw2_plan(19200, 136, 816, n_sms, out) == 0 and out[7] == 148
     assert L.cosyb200_pw2_plan(4480, 232, 1392, n_sms, out) == 0 and out[7] == 140
     assert L.cosyb200_pw2_plan(19200, 816, 136, n_sms, out) == 0 and out[8] == 0       # short K: whole tiles
+
+
+def test_multiview_host_grouping_matches_pandas():
+    """The numpy grouping of the multiview host path gives what the reference's pandas formulation gives
+    (multiview/ransac.py:119-125: groupby('obj_id') size / sum / first)."""
+    from cosypose_b200.multiview.ransac import make_obj_infos
+    from cosypose_b200.utils import tensor_collection as tc
+    rs = np.random.RandomState(0)
+    n = 57
+    infos = pd.DataFrame(dict(obj_id=rs.randint(0, 9, n), score=rs.rand(n), label=[f'obj_{i:06d}' for i in rs.randint(1, 5, n)],
+                              view_id=rs.randint(0, 4, n)))
+    got = make_obj_infos(tc.PandasTensorCollection(infos=infos, poses=torch.zeros(n, 4, 4)))
+    ref = infos.loc[:, ['obj_id', 'score', 'label']].copy()
+    gb = ref.groupby('obj_id')
+    ref['n_cand'] = gb['score'].transform('size').astype(int)
+    ref['score'] = gb['score'].transform('sum')
+    ref = ref.groupby('obj_id').first().reset_index(drop=False)
+    assert list(got.columns) == list(ref.columns) == ['obj_id', 'score', 'label', 'n_cand']
+    assert got['obj_id'].tolist() == ref['obj_id'].tolist() and got['n_cand'].tolist() == ref['n_cand'].tolist()
+    assert got['label'].tolist() == ref['label'].tolist()
+    assert np.allclose(got['score'].to_numpy(), ref['score'].to_numpy(), rtol=1e-12)
+
+
+def test_concatenate_single_collection_is_a_fresh_collection():
+    from cosypose_b200.utils import tensor_collection as tc
+    infos = pd.DataFrame(dict(a=[3, 1, 2]), index=[7, 8, 9])
+    c = tc.PandasTensorCollection(infos=infos, poses=torch.arange(3.))
+    out = tc.concatenate([c, tc.PandasTensorCollection(infos=pd.DataFrame(), poses=torch.zeros(0))])
+    assert list(out.infos.index) == [0, 1, 2] and out.infos['a'].tolist() == [3, 1, 2]
+    out.infos['b'] = 1                      # does not leak into the input
+    assert 'b' not in c.infos.columns
+    out.poses = out.poses + 1
+    assert torch.equal(c.poses, torch.arange(3.))
+
+
+def test_lazy_history_builds_scene_collections_on_first_access():
+    from cosypose_b200.multiview.bundle_adjustment import LazyHistory
+
+    class Problem:
+        calls = 0
+
+        def _scene_infos_many(self, states):
+            Problem.calls += 1
+            return [(f'objects{i}', f'cameras{i}') for i, _ in enumerate(states)]
+    h = LazyHistory(dict(TWO_9d=[1, 2, 3], TCW_9d=[4, 5, 6], loss=[0.3, 0.2, 0.1]), Problem())
+    assert h['loss'] == [0.3, 0.2, 0.1] and Problem.calls == 0           # plain keys do not trigger the conversion
+    assert 'objects' in h and 'cameras' in h and Problem.calls == 0
+    assert h['objects'] == ['objects0', 'objects1', 'objects2'] and Problem.calls == 1
+    assert h['cameras'] == ['cameras0', 'cameras1', 'cameras2'] and Problem.calls == 1
+    assert h.get('objects') == h['objects'] and h.get('missing', 5) == 5
+    import pickle
+    d = pickle.loads(pickle.dumps(h))
+    assert type(d) is dict and d['objects'] == h['objects'] and set(d) >= {'TWO_9d', 'TCW_9d', 'loss', 'objects', 'cameras'}
