@@ -46,7 +46,7 @@ def run_custom_scenario(scenario_dir, sv_score_th=0.3, n_symmetries_rot=64, rans
     candidates = bop_io.read_csv_candidates(scenario_dir / 'candidates.csv').float().to(device)
     candidates.infos['group_id'] = 0
     scene_ids = np.unique(candidates.infos['scene_id'])
-    assert len(scene_ids) == 1, 'Please only provide 6D pose estimations that correspond to the same scene.'
+    assert len(scene_ids) == 1, 'candidates.csv must hold the candidates of ONE scene'
     scene_id = scene_ids.item()
     view_ids = np.unique(candidates.infos['view_id'])
     log(f'Loaded {len(candidates)} candidates in {len(view_ids)} views.')
@@ -79,16 +79,17 @@ def run_custom_scenario(scenario_dir, sv_score_th=0.3, n_symmetries_rot=64, rans
 
 
 def main():
-    parser = argparse.ArgumentParser('CosyPose multi-view reconstruction for a custom scenario')
+    parser = argparse.ArgumentParser(description='Multi-view scene reconstruction of a scenario directory (same options as the '
+                                                 "reference's scripts/run_custom_scenario.py)")
     parser.add_argument('--scenario', required=True, type=str, help='scenario directory')
-    parser.add_argument('--sv_score_th', default=0.3, type=float, help='Score to filter single-view predictions')
+    parser.add_argument('--sv_score_th', default=0.3, type=float, help='candidates scoring below this are dropped')
     parser.add_argument('--n_symmetries_rot', default=64, type=int,
-                        help='Number of discretized symmetries to use for continuous symmetries')
-    parser.add_argument('--ransac_n_iter', default=2000, type=int, help='Max number of RANSAC iterations per pair of views')
+                        help='rotations a continuous symmetry is discretised into')
+    parser.add_argument('--ransac_n_iter', default=2000, type=int, help='RANSAC seeds per ordered view pair')
     parser.add_argument('--ransac_dist_threshold', default=0.02, type=float,
-                        help='Threshold (in meters) on symmetric distance to consider a tentative match an inlier')
-    parser.add_argument('--ba_n_iter', default=10, type=int, help='Maximum number of LM iterations in stage 3')
-    parser.add_argument('--nms_th', default=0.04, type=float, help='Threshold (meter) for NMS 3D')
+                        help='inlier bound on the symmetric distance of a tentative match, metres')
+    parser.add_argument('--ba_n_iter', default=10, type=int, help='Levenberg-Marquardt iterations of the bundle adjustment')
+    parser.add_argument('--nms_th', default=0.04, type=float, help='objects closer than this (metres) to a better one are suppressed')
     args = parser.parse_args()
     run_custom_scenario(args.scenario, args.sv_score_th, args.n_symmetries_rot, args.ransac_n_iter,
                         args.ransac_dist_threshold, args.ba_n_iter, args.nms_th)
